@@ -1,0 +1,1421 @@
+// engine.cu — the C ABI of include/advspec_engine.h: one model's weights, one
+// shared-prefix KV region and up to 8 forked opponents on one B200.
+//
+// Path (stands in for the N concurrent `completion` calls of the reference,
+// skills/adversarial-spec/scripts/models.py:628 under :681-722):
+//   prefill  : embed -> L x [rmsnorm, QKV GEMM(tcgen05), RoPE+KV write, causal
+//              attention, O GEMM(+residual), rmsnorm, gate/up GEMM(+act*up),
+//              down GEMM(+residual)] -> final norm + lm_head of the last row
+//   fork     : N opponent slots over the one prefix KV, no copy
+//   decode   : CUDA-graph-replayed step: L x [norm+QKV GEMV, RoPE+KV append,
+//              split-KV attention (prefix shared, suffix private), combine,
+//              O GEMV(+res), norm+gate/up GEMV(+act*up), down GEMV(+res)]
+//              -> norm+lm_head GEMV -> Gumbel-max sample + next embedding
+// No CPU fallback exists: every compute entry point needs a CUDA device.
+#include "../../include/advspec_engine.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "attn.cuh"
+#include "common.cuh"
+#include "decode_kernels.cuh"
+#include "gemm_tcgen05.cuh"
+
+using namespace advspec;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v, size_t a = kAlign) { return (v + a - 1) / a * a; }
+
+struct BlobLayout {
+  struct LayerOff {
+    size_t attn_norm, wqkv, bqkv, wo, mlp_norm, wgu, wd;
+  };
+  size_t embed = 0, final_norm = 0, lm_head = 0, total = 0;
+  std::vector<LayerOff> layers;
+};
+
+inline int qkv_dim(const advspec_model_desc& d) { return (d.n_heads + 2 * d.n_kv_heads) * d.head_dim; }
+
+// Order and alignment restated in adversarial-spec_b200/weights.py (checked by tests).
+BlobLayout make_layout(const advspec_model_desc& d) {
+  BlobLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes);
+    return o;
+  };
+  const size_t dm = d.d_model, qkv = qkv_dim(d), hd = (size_t)d.n_heads * d.head_dim;
+  L.embed = take((size_t)d.vocab_size * dm * 2);
+  L.layers.resize(d.n_layers);
+  for (int l = 0; l < d.n_layers; ++l) {
+    auto& o = L.layers[l];
+    o.attn_norm = take(dm * 4);
+    o.wqkv = take(qkv * dm * 2);
+    o.bqkv = d.qkv_bias ? take(qkv * 4) : (size_t)-1;
+    o.wo = take(dm * hd * 2);
+    o.mlp_norm = take(dm * 4);
+    o.wgu = take((size_t)2 * d.d_ff * dm * 2);
+    o.wd = take(dm * (size_t)d.d_ff * 2);
+  }
+  L.final_norm = take(dm * 4);
+  L.lm_head = d.tied_lm_head ? (size_t)-1 : take((size_t)d.vocab_size * dm * 2);
+  L.total = off;
+  return L;
+}
+
+bool desc_ok(const advspec_model_desc* d, std::string* why) {
+  auto bad = [&](const char* m) {
+    if (why) *why = m;
+    return false;
+  };
+  if (!d) return bad("null model desc");
+  if (d->abi_version != ADVSPEC_ABI_VERSION) return bad("abi_version mismatch");
+  if (d->n_layers < 1 || d->d_model < 8 || d->n_heads < 1 || d->n_kv_heads < 1 || d->d_ff < 8 ||
+      d->vocab_size < 2)
+    return bad("non-positive model dimension");
+  if (d->n_heads % d->n_kv_heads) return bad("n_heads must be a multiple of n_kv_heads");
+  if (d->head_dim != 64 && d->head_dim != 96 && d->head_dim != 128 && d->head_dim != 256)
+    return bad("head_dim must be 64, 96, 128 or 256");
+  if (d->d_model % 8 || d->d_ff % 8 || (d->n_heads * d->head_dim) % 8)
+    return bad("d_model, d_ff and n_heads*head_dim must be multiples of 8");
+  if (d->max_seqs < 1 || d->max_seqs > 8) return bad("max_seqs must be in 1..8");
+  if (d->max_prefix_tokens < 1 || d->max_new_tokens < 1) return bad("bad KV capacities");
+  if (d->tp_rank != 0 || d->tp_size != 1) return bad("tensor parallelism is reserved (tp_size must be 1)");
+  if (d->act != 0 && d->act != 1) return bad("act must be 0 (SiLU) or 1 (tanh GELU)");
+  return true;
+}
+
+// ------------------------------------------------------------------ TMA maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// bf16 [rows][cols] row-major with row pitch ld (elements); box = 64 cols x box_rows, 128B swizzle.
+bool make_tmap(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int g_num_sms = 0;
+int num_sms(int device) {
+  if (g_num_sms == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <typename K>
+cudaError_t set_smem(K kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+template <int BN, int EPI>
+cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int device,
+                          cudaStream_t st) {
+  static bool attr_done = false;
+  auto kern = gemm_tc_kernel<BN, EPI>;
+  if (!attr_done) {
+    cudaError_t e = set_smem(kern, GemmCfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + BN - 1) / BN);
+  const int grid = std::min(tiles, num_sms(device));
+  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+  return cudaGetLastError();
+}
+
+// C = A[M,K] * B[N,K]^T on tcgen05.  A rows / B rows are the TMA extents.
+cudaError_t launch_gemm(const void* A, int64_t lda, int64_t a_rows, const void* B, int64_t ldb,
+                        const GemmParams& p, int epi, int device, cudaStream_t st, std::string* err) {
+  if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) ||
+      (reinterpret_cast<uintptr_t>(B) & 15)) {
+    if (err) *err = "gemm: operands must be 16-byte aligned with pitches that are multiples of 8";
+    return cudaErrorInvalidValue;
+  }
+  const bool wide = p.N > 128;
+  CUtensorMap ta, tb;
+  if (!make_tmap(&ta, A, a_rows, p.K, lda, kGemmBM) ||
+      !make_tmap(&tb, B, p.N, p.K, ldb, wide ? 256 : 128)) {
+    if (err) *err = "cuTensorMapEncodeTiled failed";
+    return cudaErrorInvalidValue;
+  }
+#define ADV_GEMM_CASE(E)                                                   \
+  case E:                                                                  \
+    return wide ? launch_gemm_t<256, E>(ta, tb, p, device, st)            \
+                : launch_gemm_t<128, E>(ta, tb, p, device, st);
+  switch (epi) {
+    ADV_GEMM_CASE(EPI_BF16)
+    ADV_GEMM_CASE(EPI_RESADD_F32)
+    ADV_GEMM_CASE(EPI_GATED_BF16)
+    ADV_GEMM_CASE(EPI_F32)
+  }
+#undef ADV_GEMM_CASE
+  if (err) *err = "gemm: unknown epilogue";
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_gemm_check(const void* A, int64_t lda, const void* B, int64_t ldb,
+                              const GemmParams& p, int epi, cudaStream_t st) {
+  const int ncols = (epi == EPI_GATED_BF16) ? p.N / 2 : p.N;
+  const int64_t total = (int64_t)p.M * ncols;
+  const int grid = (int)((total + 255) / 256);
+  auto a = reinterpret_cast<const __nv_bfloat16*>(A);
+  auto b = reinterpret_cast<const __nv_bfloat16*>(B);
+  switch (epi) {
+    case EPI_BF16: gemm_check_kernel<EPI_BF16><<<grid, 256, 0, st>>>(a, lda, b, ldb, p); break;
+    case EPI_RESADD_F32: gemm_check_kernel<EPI_RESADD_F32><<<grid, 256, 0, st>>>(a, lda, b, ldb, p); break;
+    case EPI_GATED_BF16: gemm_check_kernel<EPI_GATED_BF16><<<grid, 256, 0, st>>>(a, lda, b, ldb, p); break;
+    case EPI_F32: gemm_check_kernel<EPI_F32><<<grid, 256, 0, st>>>(a, lda, b, ldb, p); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------- GEMV
+bool g_use_pdl = true;
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                       bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && g_use_pdl) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+cudaError_t launch_gemv(const GemvParams& p, int b, int device, cudaStream_t st, bool pdl) {
+  const int pairs = (p.N + 1) / 2;
+  const int grid = std::max(1, std::min(2 * num_sms(device), pairs));
+  dim3 g(grid), blk(kGemvThreads);
+  switch (b) {
+    case 1: return launch_pdl(gemv_kernel<1, 2>, g, blk, 0, st, pdl, p);
+    case 2: return launch_pdl(gemv_kernel<2, 2>, g, blk, 0, st, pdl, p);
+    case 3: return launch_pdl(gemv_kernel<3, 2>, g, blk, 0, st, pdl, p);
+    case 4: return launch_pdl(gemv_kernel<4, 2>, g, blk, 0, st, pdl, p);
+    case 5: return launch_pdl(gemv_kernel<5, 1>, g, blk, 0, st, pdl, p);
+    case 6: return launch_pdl(gemv_kernel<6, 1>, g, blk, 0, st, pdl, p);
+    case 7: return launch_pdl(gemv_kernel<7, 1>, g, blk, 0, st, pdl, p);
+    case 8: return launch_pdl(gemv_kernel<8, 1>, g, blk, 0, st, pdl, p);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// -------------------------------------------------------------- attention
+cudaError_t launch_attn_prefill(const AttnPrefillParams& p, int DH, int impl, cudaStream_t st,
+                                std::string* err) {
+  if (impl == 1 || (DH != 64 && DH != 128)) {
+    const int64_t warps = (int64_t)p.n_q * p.H;
+    const int grid = (int)((warps * 32 + 255) / 256);
+    attn_prefill_check_kernel<<<grid, 256, 0, st>>>(p, DH);
+    return cudaGetLastError();
+  }
+  dim3 grid((p.n_q + 63) / 64, p.H);
+  if (DH == 128) {
+    static bool done = false;
+    const int smem = (64 + 4 * 64) * 128 * 2;
+    if (!done) {
+      cudaError_t e = set_smem(attn_prefill_kernel<128>, smem);
+      if (e != cudaSuccess) return e;
+      done = true;
+    }
+    attn_prefill_kernel<128><<<grid, 128, smem, st>>>(p);
+  } else {
+    static bool done = false;
+    const int smem = (64 + 4 * 64) * 64 * 2;
+    if (!done) {
+      cudaError_t e = set_smem(attn_prefill_kernel<64>, smem);
+      if (e != cudaSuccess) return e;
+      done = true;
+    }
+    attn_prefill_kernel<64><<<grid, 128, smem, st>>>(p);
+  }
+  (void)err;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attn_decode(const AttnDecodeParams& p, int n_items, int DH, cudaStream_t st, bool pdl) {
+  dim3 g(n_items), blk(128);
+  switch (DH) {
+    case 64: return launch_pdl(attn_decode_kernel<64>, g, blk, 0, st, pdl, p);
+    case 96: return launch_pdl(attn_decode_kernel<96>, g, blk, 0, st, pdl, p);
+    case 128: return launch_pdl(attn_decode_kernel<128>, g, blk, 0, st, pdl, p);
+    case 256: return launch_pdl(attn_decode_kernel<256>, g, blk, 0, st, pdl, p);
+  }
+  return cudaErrorInvalidValue;
+}
+
+__global__ void advance_kernel(const int* slots, int* suf_len) {
+  pdl_wait();
+  suf_len[slots[threadIdx.x]] += 1;
+}
+__global__ void copy_logits_kernel(const float* src, float* dst, int V) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) dst[v] = src[v];
+}
+
+}  // namespace
+
+// ============================================================================
+struct advspec_engine {
+  advspec_model_desc d{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::string err;
+
+  BlobLayout lay;
+  uint8_t* w = nullptr;
+  bool weights_ready = false;
+
+  // RoPE tables
+  float *inv_freq = nullptr, *rope_cos = nullptr, *rope_sin = nullptr;
+  int max_pos = 0;
+
+  // KV: prefix [L][2][Hkv][max_prefix][DH]; suffix [L][2][max_seqs][Hkv][max_new][DH]
+  __nv_bfloat16 *pkv = nullptr, *skv = nullptr;
+  size_t pkv_layer_elems = 0, skv_layer_elems = 0;
+
+  // prefill workspaces (chunk of C tokens)
+  int C = 0;
+  int* p_tokens = nullptr;
+  float* p_x = nullptr;
+  __nv_bfloat16 *p_xn = nullptr, *p_qkv = nullptr, *p_attn = nullptr, *p_h = nullptr;
+  float* prefill_logits = nullptr;  // [V]
+
+  // decode workspaces (batch of max_seqs)
+  float *dx = nullptr, *dx_save = nullptr, *dq = nullptr, *dlogits = nullptr;
+  __nv_bfloat16 *dqkv = nullptr, *dattn = nullptr, *dh = nullptr;
+  float *part_m = nullptr, *part_l = nullptr, *part_o = nullptr;
+  AttnItem* items = nullptr;
+  int items_cap = 0, n_items = 0, n_slots = 0;
+
+  // opponent state (device arrays indexed by slot)
+  int *s_slots = nullptr, *s_forced = nullptr;  // [max_seqs] batch -> slot / forced tokens
+  uint64_t* s_seeds = nullptr;
+  int *s_suf_len = nullptr, *s_n_out = nullptr, *s_done = nullptr, *s_cur_tok = nullptr,
+      *s_out = nullptr;
+
+  // host-side bookkeeping
+  int prefix_gen = 0;     // id of the live prefix (0 = none)
+  int prefix_len = 0;
+  bool slot_used[8] = {false, false, false, false, false, false, false, false};
+  std::vector<int> h_suf_len = std::vector<int>(8, 0);
+  bool logits_broadcast = true;  // current logits are the prefill's (shared) ones
+  std::vector<int> logits_slots;  // batch order of dlogits when !logits_broadcast
+
+  // decode graph cache
+  cudaGraphExec_t graph = nullptr;
+  std::vector<int> graph_key;
+
+  // timing
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  advspec_timing tm{};
+  int64_t launches = 0;
+  int debug_flags = 0;  // bit0: check GEMM instead of tcgen05; bit1: scalar attention (tests only)
+  bool use_graph = true;
+
+  bool fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return false;
+  }
+  const uint8_t* wp(size_t off) const { return w + off; }
+};
+
+#define E_CUDA(e, call)                                                                 \
+  do {                                                                                  \
+    cudaError_t _err = (call);                                                          \
+    if (_err != cudaSuccess) {                                                          \
+      (e)->fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_err), __FILE__, __LINE__); \
+      return (_err == cudaErrorMemoryAllocation) ? ADVSPEC_ERR_OOM : ADVSPEC_ERR_CUDA;  \
+    }                                                                                   \
+  } while (0)
+
+namespace {
+
+advspec_status check_watchdog(advspec_engine* e) {
+  unsigned int code = 0;
+  E_CUDA(e, cudaMemcpyFromSymbol(&code, g_watchdog_code, sizeof code));
+  if (code != 0) {
+    e->fail("device watchdog tripped: mbarrier wait timed out at site 0x%x", code & 0x7fffffffu);
+    unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_watchdog_code, &zero, sizeof zero);
+    return ADVSPEC_ERR_KERNEL;
+  }
+  return ADVSPEC_OK;
+}
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t n) {
+  return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
+}
+
+__nv_bfloat16* prefix_k(advspec_engine* e, int layer) { return e->pkv + (size_t)layer * 2 * e->pkv_layer_elems; }
+__nv_bfloat16* prefix_v(advspec_engine* e, int layer) { return prefix_k(e, layer) + e->pkv_layer_elems; }
+__nv_bfloat16* suffix_k(advspec_engine* e, int layer) { return e->skv + (size_t)layer * 2 * e->skv_layer_elems; }
+__nv_bfloat16* suffix_v(advspec_engine* e, int layer) { return suffix_k(e, layer) + e->skv_layer_elems; }
+
+struct LayerW {
+  const float* attn_norm;
+  const __nv_bfloat16* wqkv;
+  const float* bqkv;
+  const __nv_bfloat16* wo;
+  const float* mlp_norm;
+  const __nv_bfloat16* wgu;
+  const __nv_bfloat16* wd;
+};
+LayerW layer_w(advspec_engine* e, int l) {
+  const auto& o = e->lay.layers[l];
+  LayerW r;
+  r.attn_norm = reinterpret_cast<const float*>(e->wp(o.attn_norm));
+  r.wqkv = reinterpret_cast<const __nv_bfloat16*>(e->wp(o.wqkv));
+  r.bqkv = e->d.qkv_bias ? reinterpret_cast<const float*>(e->wp(o.bqkv)) : nullptr;
+  r.wo = reinterpret_cast<const __nv_bfloat16*>(e->wp(o.wo));
+  r.mlp_norm = reinterpret_cast<const float*>(e->wp(o.mlp_norm));
+  r.wgu = reinterpret_cast<const __nv_bfloat16*>(e->wp(o.wgu));
+  r.wd = reinterpret_cast<const __nv_bfloat16*>(e->wp(o.wd));
+  return r;
+}
+const __nv_bfloat16* embed_w(advspec_engine* e) { return reinterpret_cast<const __nv_bfloat16*>(e->wp(e->lay.embed)); }
+const __nv_bfloat16* lm_head_w(advspec_engine* e) {
+  return e->d.tied_lm_head ? embed_w(e) : reinterpret_cast<const __nv_bfloat16*>(e->wp(e->lay.lm_head));
+}
+const float* final_norm_w(advspec_engine* e) { return reinterpret_cast<const float*>(e->wp(e->lay.final_norm)); }
+
+// One GEMM of the prefill path (tcgen05 unless the test-only debug flag asks for the check kernel).
+advspec_status prefill_gemm(advspec_engine* e, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B,
+                            int64_t ldb, void* C, int64_t ldc, const float* bias, int M, int N, int K,
+                            int epi) {
+  GemmParams p{C, ldc, bias, M, N, K, e->d.act};
+  if (e->debug_flags & 1) {
+    E_CUDA(e, launch_gemm_check(A, lda, B, ldb, p, epi, e->stream));
+  } else {
+    std::string why;
+    // the activation buffers hold C rows, so the TMA extent may cover whole 128-row tiles
+    const int64_t a_rows = std::min<int64_t>((M + kGemmBM - 1) / kGemmBM * kGemmBM, e->C);
+    cudaError_t r = launch_gemm(A, lda, a_rows, B, ldb, p, epi, e->device, e->stream, &why);
+    if (r != cudaSuccess) {
+      e->fail("prefill gemm M=%d N=%d K=%d failed: %s %s", M, N, K, cudaGetErrorString(r), why.c_str());
+      return ADVSPEC_ERR_CUDA;
+    }
+  }
+  e->launches++;
+  return ADVSPEC_OK;
+}
+
+// Runs the transformer layers over `m` prompt tokens at positions pos0.. (tokens
+// already in p_tokens), leaving the fp32 residual stream in p_x.
+advspec_status prefill_chunk(advspec_engine* e, int m, int pos0) {
+  const auto& d = e->d;
+  const int dm = d.d_model, QKV = qkv_dim(d), HD = d.n_heads * d.head_dim;
+  embed_kernel<<<m, 256, 0, e->stream>>>(e->p_tokens, embed_w(e), e->p_x, dm, d.embed_scale);
+  E_CUDA(e, cudaGetLastError());
+  e->launches++;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const LayerW w = layer_w(e, l);
+    rmsnorm_kernel<<<m, 256, 0, e->stream>>>(e->p_x, w.attn_norm, e->p_xn, dm, d.norm_eps);
+    E_CUDA(e, cudaGetLastError());
+    advspec_status s = prefill_gemm(e, e->p_xn, dm, w.wqkv, dm, e->p_qkv, QKV, w.bqkv, m, QKV, dm, EPI_BF16);
+    if (s) return s;
+    rope_prefill_kernel<<<m, 256, 0, e->stream>>>(e->p_qkv, QKV, prefix_k(e, l), prefix_v(e, l),
+                                                   d.max_prefix_tokens, e->rope_cos, e->rope_sin, pos0,
+                                                   d.n_heads, d.n_kv_heads, d.head_dim);
+    E_CUDA(e, cudaGetLastError());
+    AttnPrefillParams ap{e->p_qkv, QKV, prefix_k(e, l), prefix_v(e, l), d.max_prefix_tokens, e->p_attn,
+                         m, pos0, d.n_heads, d.n_kv_heads, 1.0f / sqrtf((float)d.head_dim)};
+    E_CUDA(e, launch_attn_prefill(ap, d.head_dim, (e->debug_flags & 2) ? 1 : 0, e->stream, nullptr));
+    s = prefill_gemm(e, e->p_attn, HD, w.wo, HD, e->p_x, dm, nullptr, m, dm, HD, EPI_RESADD_F32);
+    if (s) return s;
+    rmsnorm_kernel<<<m, 256, 0, e->stream>>>(e->p_x, w.mlp_norm, e->p_xn, dm, d.norm_eps);
+    E_CUDA(e, cudaGetLastError());
+    s = prefill_gemm(e, e->p_xn, dm, w.wgu, dm, e->p_h, d.d_ff, nullptr, m, 2 * d.d_ff, dm, EPI_GATED_BF16);
+    if (s) return s;
+    s = prefill_gemm(e, e->p_h, d.d_ff, w.wd, d.d_ff, e->p_x, dm, nullptr, m, dm, d.d_ff, EPI_RESADD_F32);
+    if (s) return s;
+    e->launches += 4;
+  }
+  return ADVSPEC_OK;
+}
+
+void free_all(advspec_engine* e) {
+  cudaSetDevice(e->device);
+  if (e->graph) cudaGraphExecDestroy(e->graph);
+  void* ptrs[] = {e->w, e->inv_freq, e->rope_cos, e->rope_sin, e->pkv, e->skv, e->p_tokens, e->p_x,
+                  e->p_xn, e->p_qkv, e->p_attn, e->p_h, e->prefill_logits, e->dx, e->dx_save, e->dq,
+                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->items,
+                  e->s_slots, e->s_forced, e->s_seeds, e->s_suf_len, e->s_n_out, e->s_done,
+                  e->s_cur_tok, e->s_out};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+}
+
+// Attention work items for a decode call of batch `slots` over the live prefix.
+void build_items(advspec_engine* e, const std::vector<int>& slots, std::vector<AttnItem>* out,
+                 int* n_slots) {
+  const auto& d = e->d;
+  const int b = (int)slots.size();
+  const int G = d.n_heads / d.n_kv_heads;
+  // rows of one KV head over the shared prefix: (batch, head) for every opponent
+  const int rows = b * G;
+  const int nrg = (rows + 3) / 4;
+  int n_splits = std::max(1, (2 * num_sms(e->device)) / std::max(1, d.n_kv_heads * nrg));
+  n_splits = std::min(n_splits, std::max(1, e->prefix_len / 256));
+  *n_slots = n_splits + 1;
+  out->clear();
+  for (int hk = 0; hk < d.n_kv_heads; ++hk) {
+    for (int rg = 0; rg < nrg; ++rg) {
+      for (int s = 0; s < n_splits; ++s) {
+        AttnItem it{};
+        it.kv_head = hk;
+        it.seq = -1;
+        it.tok_begin = (int)((int64_t)e->prefix_len * s / n_splits);
+        it.tok_end = (int)((int64_t)e->prefix_len * (s + 1) / n_splits);
+        it.slot = s;
+        it.n_rows = 0;
+        for (int r = rg * 4; r < std::min(rows, rg * 4 + 4); ++r) {
+          it.row_b[it.n_rows] = r / G;
+          it.row_head[it.n_rows] = hk * G + r % G;
+          it.n_rows++;
+        }
+        out->push_back(it);
+      }
+    }
+  }
+  for (int bi = 0; bi < b; ++bi) {
+    for (int hk = 0; hk < d.n_kv_heads; ++hk) {
+      for (int g0 = 0; g0 < G; g0 += 4) {
+        AttnItem it{};
+        it.kv_head = hk;
+        it.seq = slots[bi];
+        it.slot = n_splits;
+        it.n_rows = 0;
+        for (int g = g0; g < std::min(G, g0 + 4); ++g) {
+          it.row_b[it.n_rows] = bi;
+          it.row_head[it.n_rows] = hk * G + g;
+          it.n_rows++;
+        }
+        out->push_back(it);
+      }
+    }
+  }
+}
+
+// Enqueue one forward step (all layers + lm_head) for the batch in s_slots.
+advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
+  const auto& d = e->d;
+  const int dm = d.d_model, QKV = qkv_dim(d), HD = d.n_heads * d.head_dim;
+  const bool prof = gemv_ms_out != nullptr;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+  auto gemv = [&](const GemvParams& gp) -> cudaError_t {
+    cudaEvent_t a = nullptr, z = nullptr;
+    if (prof) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&z);
+      cudaEventRecord(a, e->stream);
+    }
+    cudaError_t r = launch_gemv(gp, b, e->device, e->stream, !prof);
+    if (prof) {
+      cudaEventRecord(z, e->stream);
+      evs.emplace_back(a, z);
+    }
+    e->launches++;
+    return r;
+  };
+  for (int l = 0; l < d.n_layers; ++l) {
+    const LayerW w = layer_w(e, l);
+    GemvParams g1{w.wqkv, e->dx, w.attn_norm, w.bqkv, e->dqkv, QKV, dm, 1, EPI_BF16, d.act, d.norm_eps};
+    E_CUDA(e, gemv(g1));
+    E_CUDA(e, launch_pdl(rope_decode_kernel, dim3(b), dim3(256), 0, e->stream, true,
+                         (const __nv_bfloat16*)e->dqkv, e->dq, suffix_k(e, l), suffix_v(e, l),
+                         (int64_t)d.max_new_tokens, (const int*)e->s_slots, (const int*)e->s_suf_len,
+                         e->prefix_len, (const float*)e->rope_cos, (const float*)e->rope_sin, d.n_heads,
+                         d.n_kv_heads, d.head_dim));
+    AttnDecodeParams ap{};
+    ap.items = e->items;
+    ap.q = e->dq;
+    ap.pk = prefix_k(e, l);
+    ap.pv = prefix_v(e, l);
+    ap.pstride = d.max_prefix_tokens;
+    ap.sk = suffix_k(e, l);
+    ap.sv = suffix_v(e, l);
+    ap.sstride = d.max_new_tokens;
+    ap.suf_len = e->s_suf_len;
+    ap.part_m = e->part_m;
+    ap.part_l = e->part_l;
+    ap.part_o = e->part_o;
+    ap.H = d.n_heads;
+    ap.Hkv = d.n_kv_heads;
+    ap.n_slots = e->n_slots;
+    ap.scale = 1.0f / sqrtf((float)d.head_dim);
+    E_CUDA(e, launch_attn_decode(ap, e->n_items, d.head_dim, e->stream, true));
+    E_CUDA(e, launch_pdl(attn_decode_combine_kernel, dim3(b * d.n_heads), dim3(128), 0, e->stream, true,
+                         (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o,
+                         e->dattn, e->n_slots, d.head_dim));
+    GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, EPI_RESADD_F32, d.act, d.norm_eps};
+    E_CUDA(e, gemv(g2));
+    GemvParams g3{w.wgu, e->dx, w.mlp_norm, nullptr, e->dh, 2 * d.d_ff, dm, 1, EPI_GATED_BF16, d.act, d.norm_eps};
+    E_CUDA(e, gemv(g3));
+    GemvParams g4{w.wd, e->dh, nullptr, nullptr, e->dx, dm, d.d_ff, 0, EPI_RESADD_F32, d.act, d.norm_eps};
+    E_CUDA(e, gemv(g4));
+    e->launches += 3;
+  }
+  GemvParams gl{lm_head_w(e), e->dx, final_norm_w(e), nullptr, e->dlogits, d.vocab_size, dm, 1, EPI_F32,
+                d.act, d.norm_eps};
+  E_CUDA(e, gemv(gl));
+  if (prof) {
+    E_CUDA(e, cudaStreamSynchronize(e->stream));
+    float total = 0.f;
+    for (auto& pr : evs) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pr.first, pr.second);
+      total += ms;
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    *gemv_ms_out = total;
+    e->tm.gemv_launches = (int)evs.size();
+  }
+  return ADVSPEC_OK;
+}
+
+SampleParams make_sample_params(advspec_engine* e, float temperature, int eos_id, bool broadcast,
+                                bool advance, const int* forced, bool record) {
+  SampleParams sp{};
+  sp.logits = broadcast ? e->prefill_logits : e->dlogits;
+  sp.broadcast_logits = broadcast ? 1 : 0;
+  sp.V = e->d.vocab_size;
+  sp.temperature = temperature;
+  sp.slots = e->s_slots;
+  sp.seeds = e->s_seeds;
+  sp.suf_len = e->s_suf_len;
+  sp.n_out = e->s_n_out;
+  sp.done = e->s_done;
+  sp.out_tokens = record ? e->s_out : nullptr;
+  sp.out_stride = e->d.max_new_tokens;
+  sp.eos_id = eos_id;
+  sp.advance = advance ? 1 : 0;
+  sp.forced = forced;
+  sp.cur_tok = e->s_cur_tok;
+  sp.embed = embed_w(e);
+  sp.x = e->dx;
+  sp.d = e->d.d_model;
+  sp.embed_scale = e->d.embed_scale;
+  return sp;
+}
+
+advspec_status setup_batch(advspec_engine* e, const int32_t* seq_ids, int n, std::vector<int>* slots) {
+  if (!seq_ids || n < 1 || n > e->d.max_seqs) {
+    e->fail("batch size %d outside 1..%d", n, e->d.max_seqs);
+    return ADVSPEC_ERR_INVALID;
+  }
+  if (e->prefix_gen == 0) {
+    e->fail("no live prefix: call advspec_prefill first");
+    return ADVSPEC_ERR_STATE;
+  }
+  slots->clear();
+  for (int i = 0; i < n; ++i) {
+    const int s = seq_ids[i];
+    if (s < 0 || s >= e->d.max_seqs || !e->slot_used[s]) {
+      e->fail("seq id %d is not a live opponent", s);
+      return ADVSPEC_ERR_STATE;
+    }
+    for (int j = 0; j < i; ++j)
+      if (seq_ids[j] == s) {
+        e->fail("seq id %d listed twice", s);
+        return ADVSPEC_ERR_INVALID;
+      }
+    slots->push_back(s);
+  }
+  E_CUDA(e, cudaMemcpyAsync(e->s_slots, slots->data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  std::vector<AttnItem> items;
+  build_items(e, *slots, &items, &e->n_slots);
+  if ((int)items.size() > e->items_cap) {
+    e->fail("internal: %zu attention items exceed capacity %d", items.size(), e->items_cap);
+    return ADVSPEC_ERR_INVALID;
+  }
+  e->n_items = (int)items.size();
+  E_CUDA(e, cudaMemcpyAsync(e->items, items.data(), items.size() * sizeof(AttnItem), cudaMemcpyHostToDevice,
+                            e->stream));
+  E_CUDA(e, cudaStreamSynchronize(e->stream));  // items/slots vectors die with this scope
+  return ADVSPEC_OK;
+}
+
+}  // namespace
+
+// ============================================================================
+extern "C" {
+
+size_t advspec_weight_blob_bytes(const advspec_model_desc* desc) {
+  if (!desc_ok(desc, nullptr)) return 0;
+  return make_layout(*desc).total;
+}
+
+size_t advspec_weight_offset(const advspec_model_desc* desc, int32_t layer, const char* name) {
+  if (!desc_ok(desc, nullptr) || !name) return (size_t)-1;
+  const BlobLayout L = make_layout(*desc);
+  const std::string n(name);
+  if (layer < 0) {
+    if (n == "embed") return L.embed;
+    if (n == "final_norm") return L.final_norm;
+    if (n == "lm_head") return L.lm_head;
+    return (size_t)-1;
+  }
+  if (layer >= desc->n_layers) return (size_t)-1;
+  const auto& o = L.layers[layer];
+  if (n == "attn_norm") return o.attn_norm;
+  if (n == "wqkv") return o.wqkv;
+  if (n == "bqkv") return o.bqkv;
+  if (n == "wo") return o.wo;
+  if (n == "mlp_norm") return o.mlp_norm;
+  if (n == "wgu") return o.wgu;
+  if (n == "wd") return o.wd;
+  return (size_t)-1;
+}
+
+const char* advspec_last_error(const advspec_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t device, advspec_engine** out) {
+  if (!out) return ADVSPEC_ERR_INVALID;
+  *out = nullptr;
+  std::string why;
+  if (!desc_ok(desc, &why)) {
+    g_create_error = why;
+    return ADVSPEC_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device || device < 0) {
+    g_create_error = "no CUDA device " + std::to_string(device) + " (this engine has no CPU fallback)";
+    return ADVSPEC_ERR_CUDA;
+  }
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                     "; this library carries sm_100a code only";
+    return ADVSPEC_ERR_CUDA;
+  }
+  advspec_engine* e = new advspec_engine();
+  e->d = *desc;
+  e->device = device;
+  e->lay = make_layout(*desc);
+  const char* dbg = getenv("ADVSPEC_DEBUG_FLAGS");
+  e->debug_flags = dbg ? atoi(dbg) : 0;
+  e->use_graph = getenv("ADVSPEC_NO_GRAPH") == nullptr;
+  g_use_pdl = getenv("ADVSPEC_NO_PDL") == nullptr;
+
+  auto boot = [&]() -> advspec_status {
+    const auto& d = e->d;
+    E_CUDA(e, cudaSetDevice(device));
+    E_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    E_CUDA(e, cudaEventCreate(&e->ev0));
+    E_CUDA(e, cudaEventCreate(&e->ev1));
+    E_CUDA(e, dmalloc(&e->w, e->lay.total));
+    const int half = d.head_dim / 2;
+    e->max_pos = d.max_prefix_tokens + d.max_new_tokens;
+    E_CUDA(e, dmalloc(&e->inv_freq, half));
+    E_CUDA(e, dmalloc(&e->rope_cos, (size_t)e->max_pos * half));
+    E_CUDA(e, dmalloc(&e->rope_sin, (size_t)e->max_pos * half));
+    e->pkv_layer_elems = (size_t)d.n_kv_heads * d.max_prefix_tokens * d.head_dim;
+    e->skv_layer_elems = (size_t)d.max_seqs * d.n_kv_heads * d.max_new_tokens * d.head_dim;
+    E_CUDA(e, dmalloc(&e->pkv, (size_t)d.n_layers * 2 * e->pkv_layer_elems));
+    E_CUDA(e, dmalloc(&e->skv, (size_t)d.n_layers * 2 * e->skv_layer_elems));
+    e->C = std::min(4096, (d.max_prefix_tokens + 127) / 128 * 128);
+    const size_t C = e->C, dm = d.d_model, QKV = qkv_dim(d), HD = (size_t)d.n_heads * d.head_dim;
+    E_CUDA(e, dmalloc(&e->p_tokens, C));
+    E_CUDA(e, dmalloc(&e->p_x, C * dm));
+    E_CUDA(e, dmalloc(&e->p_xn, C * dm));
+    E_CUDA(e, dmalloc(&e->p_qkv, C * QKV));
+    E_CUDA(e, dmalloc(&e->p_attn, C * HD));
+    E_CUDA(e, dmalloc(&e->p_h, C * (size_t)d.d_ff));
+    E_CUDA(e, cudaMemsetAsync(e->p_xn, 0, C * dm * 2, e->stream));
+    E_CUDA(e, cudaMemsetAsync(e->p_attn, 0, C * HD * 2, e->stream));
+    E_CUDA(e, cudaMemsetAsync(e->p_h, 0, C * (size_t)d.d_ff * 2, e->stream));
+    E_CUDA(e, dmalloc(&e->prefill_logits, (size_t)d.vocab_size));
+    const size_t B = d.max_seqs;
+    E_CUDA(e, dmalloc(&e->dx, B * dm));
+    E_CUDA(e, dmalloc(&e->dx_save, B * dm));
+    E_CUDA(e, dmalloc(&e->dq, B * HD));
+    E_CUDA(e, dmalloc(&e->dlogits, B * (size_t)d.vocab_size));
+    E_CUDA(e, dmalloc(&e->dqkv, B * QKV));
+    E_CUDA(e, dmalloc(&e->dattn, B * HD));
+    E_CUDA(e, dmalloc(&e->dh, B * (size_t)d.d_ff));
+    const int G = d.n_heads / d.n_kv_heads;
+    const int max_splits = 2 * 148 + 1;
+    E_CUDA(e, dmalloc(&e->part_m, B * d.n_heads * (size_t)(max_splits + 1)));
+    E_CUDA(e, dmalloc(&e->part_l, B * d.n_heads * (size_t)(max_splits + 1)));
+    E_CUDA(e, dmalloc(&e->part_o, B * d.n_heads * (size_t)(max_splits + 1) * d.head_dim));
+    e->items_cap = d.n_kv_heads * (((int)B * G + 3) / 4) * max_splits + (int)B * d.n_kv_heads * ((G + 3) / 4);
+    E_CUDA(e, dmalloc(&e->items, (size_t)e->items_cap));
+    E_CUDA(e, dmalloc(&e->s_slots, B));
+    E_CUDA(e, dmalloc(&e->s_forced, B));
+    E_CUDA(e, dmalloc(&e->s_seeds, B));
+    E_CUDA(e, dmalloc(&e->s_suf_len, B));
+    E_CUDA(e, dmalloc(&e->s_n_out, B));
+    E_CUDA(e, dmalloc(&e->s_done, B));
+    E_CUDA(e, dmalloc(&e->s_cur_tok, B));
+    E_CUDA(e, dmalloc(&e->s_out, B * (size_t)d.max_new_tokens));
+    E_CUDA(e, cudaMemsetAsync(e->s_suf_len, 0, B * sizeof(int), e->stream));
+    E_CUDA(e, cudaMemsetAsync(e->s_n_out, 0, B * sizeof(int), e->stream));
+    E_CUDA(e, cudaMemsetAsync(e->s_done, 0, B * sizeof(int), e->stream));
+    // default RoPE frequencies: theta^(-2i/head_dim), fp32 like the oracle
+    std::vector<float> inv(half);
+    for (int i = 0; i < half; ++i)
+      inv[i] = 1.0f / powf(d.rope_theta, (float)(2 * i) / (float)d.head_dim);
+    E_CUDA(e, cudaMemcpyAsync(e->inv_freq, inv.data(), half * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    const int64_t tot = (int64_t)e->max_pos * half;
+    rope_table_kernel<<<(int)((tot + 255) / 256), 256, 0, e->stream>>>(e->inv_freq, e->rope_cos, e->rope_sin,
+                                                                      e->max_pos, half);
+    E_CUDA(e, cudaGetLastError());
+    E_CUDA(e, cudaStreamSynchronize(e->stream));
+    return ADVSPEC_OK;
+  };
+  advspec_status s = boot();
+  if (s != ADVSPEC_OK) {
+    g_create_error = e->err;
+    free_all(e);
+    delete e;
+    return s;
+  }
+  *out = e;
+  return ADVSPEC_OK;
+}
+
+void advspec_engine_destroy(advspec_engine* e) {
+  if (!e) return;
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    free_all(e);
+  }
+  delete e;
+}
+
+advspec_status advspec_load_weights(advspec_engine* e, const void* host_blob, size_t bytes) {
+  if (!e) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!host_blob || bytes != e->lay.total) {
+    e->fail("weight blob is %zu bytes, expected %zu", bytes, e->lay.total);
+    return ADVSPEC_ERR_INVALID;
+  }
+  E_CUDA(e, cudaSetDevice(e->device));
+  E_CUDA(e, cudaMemcpyAsync(e->w, host_blob, bytes, cudaMemcpyHostToDevice, e->stream));
+  E_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->weights_ready = true;
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_init_weights_random(advspec_engine* e, uint64_t seed, float std) {
+  if (!e) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  E_CUDA(e, cudaSetDevice(e->device));
+  const auto& d = e->d;
+  auto rnd = [&](size_t off, size_t n, uint64_t tag) {
+    init_normal_bf16_kernel<<<1184, 256, 0, e->stream>>>(reinterpret_cast<__nv_bfloat16*>(e->w + off),
+                                                         (int64_t)n, mix64(seed ^ tag), std);
+  };
+  auto ones = [&](size_t off, size_t n, float v) {
+    fill_f32_kernel<<<64, 256, 0, e->stream>>>(reinterpret_cast<float*>(e->w + off), (int64_t)n, v);
+  };
+  const size_t dm = d.d_model, QKV = qkv_dim(d), HD = (size_t)d.n_heads * d.head_dim;
+  rnd(e->lay.embed, (size_t)d.vocab_size * dm, 1);
+  for (int l = 0; l < d.n_layers; ++l) {
+    const auto& o = e->lay.layers[l];
+    const uint64_t t = 16 * (uint64_t)(l + 1);
+    ones(o.attn_norm, dm, 1.0f);
+    rnd(o.wqkv, QKV * dm, t + 1);
+    if (d.qkv_bias) ones(o.bqkv, QKV, 0.0f);
+    rnd(o.wo, dm * HD, t + 2);
+    ones(o.mlp_norm, dm, 1.0f);
+    rnd(o.wgu, (size_t)2 * d.d_ff * dm, t + 3);
+    rnd(o.wd, dm * (size_t)d.d_ff, t + 4);
+  }
+  ones(e->lay.final_norm, dm, 1.0f);
+  if (!d.tied_lm_head) rnd(e->lay.lm_head, (size_t)d.vocab_size * dm, 2);
+  E_CUDA(e, cudaGetLastError());
+  E_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->weights_ready = true;
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_set_rope_inv_freq(advspec_engine* e, const float* inv_freq, int32_t n) {
+  if (!e) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  const int half = e->d.head_dim / 2;
+  if (!inv_freq || n != half) {
+    e->fail("inv_freq must have head_dim/2 = %d entries", half);
+    return ADVSPEC_ERR_INVALID;
+  }
+  E_CUDA(e, cudaSetDevice(e->device));
+  E_CUDA(e, cudaMemcpyAsync(e->inv_freq, inv_freq, half * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  const int64_t tot = (int64_t)e->max_pos * half;
+  rope_table_kernel<<<(int)((tot + 255) / 256), 256, 0, e->stream>>>(e->inv_freq, e->rope_cos, e->rope_sin,
+                                                                    e->max_pos, half);
+  E_CUDA(e, cudaGetLastError());
+  E_CUDA(e, cudaStreamSynchronize(e->stream));
+  return ADVSPEC_OK;
+}
+
+static advspec_status prefill_impl(advspec_engine* e, const int32_t* tokens, int32_t n, float* all_logits_host) {
+  const auto& d = e->d;
+  if (!e->weights_ready) {
+    e->fail("weights not loaded");
+    return ADVSPEC_ERR_STATE;
+  }
+  if (!tokens || n < 1 || n > d.max_prefix_tokens) {
+    e->fail("prompt of %d tokens outside 1..%d", n, d.max_prefix_tokens);
+    return ADVSPEC_ERR_INVALID;
+  }
+  for (int i = 0; i < n; ++i)
+    if (tokens[i] < 0 || tokens[i] >= d.vocab_size) {
+      e->fail("token %d at position %d outside the vocabulary", tokens[i], i);
+      return ADVSPEC_ERR_INVALID;
+    }
+  E_CUDA(e, cudaSetDevice(e->device));
+  // a new prompt replaces the live prefix and every opponent forked from it
+  e->prefix_gen = 0;
+  for (bool& u : e->slot_used) u = false;
+  float* all_logits_dev = nullptr;
+  if (all_logits_host) {
+    const size_t bytes = (size_t)n * d.vocab_size * sizeof(float);
+    if (bytes > ((size_t)4 << 30)) {
+      e->fail("advspec_prefill_logits: %zu bytes of logits is beyond the diagnostic limit", bytes);
+      return ADVSPEC_ERR_INVALID;
+    }
+    E_CUDA(e, cudaMalloc(reinterpret_cast<void**>(&all_logits_dev), bytes));
+  }
+  E_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  advspec_status st = ADVSPEC_OK;
+  for (int c0 = 0; c0 < n && st == ADVSPEC_OK; c0 += e->C) {
+    const int m = std::min(e->C, n - c0);
+    cudaError_t ce = cudaMemcpyAsync(e->p_tokens, tokens + c0, m * sizeof(int), cudaMemcpyHostToDevice, e->stream);
+    if (ce != cudaSuccess) {
+      e->fail("token upload failed: %s", cudaGetErrorString(ce));
+      st = ADVSPEC_ERR_CUDA;
+      break;
+    }
+    st = prefill_chunk(e, m, c0);
+    if (st != ADVSPEC_OK) break;
+    if (all_logits_dev) {
+      rmsnorm_kernel<<<m, 256, 0, e->stream>>>(e->p_x, final_norm_w(e), e->p_xn, d.d_model, d.norm_eps);
+      st = prefill_gemm(e, e->p_xn, d.d_model, lm_head_w(e), d.d_model,
+                        all_logits_dev + (size_t)c0 * d.vocab_size, d.vocab_size, nullptr, m, d.vocab_size,
+                        d.d_model, EPI_F32);
+    }
+    if (c0 + m == n && st == ADVSPEC_OK) {
+      // next-token logits of the last prompt position: fused final-norm + lm_head GEMV
+      GemvParams gl{lm_head_w(e), e->p_x + (size_t)(m - 1) * d.d_model, final_norm_w(e), nullptr,
+                    e->prefill_logits, d.vocab_size, d.d_model, 1, EPI_F32, d.act, d.norm_eps};
+      cudaError_t r = launch_gemv(gl, 1, e->device, e->stream, false);
+      e->launches++;
+      if (r != cudaSuccess) {
+        e->fail("lm_head gemv failed: %s", cudaGetErrorString(r));
+        st = ADVSPEC_ERR_CUDA;
+      }
+    }
+  }
+  if (st == ADVSPEC_OK) {
+    cudaEventRecord(e->ev1, e->stream);
+    cudaError_t r = cudaStreamSynchronize(e->stream);
+    if (r != cudaSuccess) {
+      e->fail("prefill failed on the device: %s", cudaGetErrorString(r));
+      st = ADVSPEC_ERR_CUDA;
+    } else {
+      cudaEventElapsedTime(&e->tm.prefill_ms, e->ev0, e->ev1);
+      st = check_watchdog(e);
+    }
+  }
+  if (st == ADVSPEC_OK && all_logits_host) {
+    cudaError_t r = cudaMemcpy(all_logits_host, all_logits_dev, (size_t)n * d.vocab_size * sizeof(float),
+                               cudaMemcpyDeviceToHost);
+    if (r != cudaSuccess) {
+      e->fail("logits download failed: %s", cudaGetErrorString(r));
+      st = ADVSPEC_ERR_CUDA;
+    }
+  }
+  if (all_logits_dev) cudaFree(all_logits_dev);
+  return st;
+}
+
+advspec_status advspec_prefill(advspec_engine* e, const int32_t* tokens, int32_t n_tokens, int32_t* prefix_id) {
+  if (!e || !prefix_id) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  advspec_status st = prefill_impl(e, tokens, n_tokens, nullptr);
+  if (st != ADVSPEC_OK) return st;
+  static int next_gen = 1;
+  e->prefix_gen = next_gen++;
+  e->prefix_len = n_tokens;
+  e->logits_broadcast = true;
+  *prefix_id = e->prefix_gen;
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_prefill_logits(advspec_engine* e, const int32_t* tokens, int32_t n_tokens, float* out) {
+  if (!e || !out) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  return prefill_impl(e, tokens, n_tokens, out);
+}
+
+advspec_status advspec_fork(advspec_engine* e, int32_t prefix_id, int32_t n_seqs, const uint64_t* seeds,
+                            int32_t* seq_ids) {
+  if (!e || !seeds || !seq_ids) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->prefix_gen == 0 || prefix_id != e->prefix_gen) {
+    e->fail("prefix %d is not live", prefix_id);
+    return ADVSPEC_ERR_STATE;
+  }
+  int free_slots = 0;
+  for (int s = 0; s < e->d.max_seqs; ++s) free_slots += e->slot_used[s] ? 0 : 1;
+  if (n_seqs < 1 || n_seqs > free_slots) {
+    e->fail("cannot fork %d opponents: %d slots free", n_seqs, free_slots);
+    return ADVSPEC_ERR_INVALID;
+  }
+  E_CUDA(e, cudaSetDevice(e->device));
+  int k = 0;
+  for (int s = 0; s < e->d.max_seqs && k < n_seqs; ++s) {
+    if (e->slot_used[s]) continue;
+    e->slot_used[s] = true;
+    const int zero = 0;
+    E_CUDA(e, cudaMemcpyAsync(e->s_seeds + s, &seeds[k], sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+    E_CUDA(e, cudaMemcpyAsync(e->s_suf_len + s, &zero, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    E_CUDA(e, cudaMemcpyAsync(e->s_n_out + s, &zero, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    E_CUDA(e, cudaMemcpyAsync(e->s_done + s, &zero, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    E_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->h_suf_len[s] = 0;
+    seq_ids[k++] = s;
+  }
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_release_seqs(advspec_engine* e, const int32_t* seq_ids, int32_t n) {
+  if (!e || !seq_ids) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  for (int i = 0; i < n; ++i)
+    if (seq_ids[i] >= 0 && seq_ids[i] < e->d.max_seqs) e->slot_used[seq_ids[i]] = false;
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_release_prefix(advspec_engine* e, int32_t prefix_id) {
+  if (!e) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (prefix_id == e->prefix_gen) {
+    e->prefix_gen = 0;
+    for (bool& u : e->slot_used) u = false;
+  }
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t n, int32_t max_new,
+                              float temperature, int32_t eos_id, int32_t* out_tokens, int32_t* out_lens) {
+  if (!e || !out_tokens || !out_lens) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  const auto& d = e->d;
+  E_CUDA(e, cudaSetDevice(e->device));
+  std::vector<int> slots;
+  advspec_status st = setup_batch(e, seq_ids, n, &slots);
+  if (st != ADVSPEC_OK) return st;
+  int room = d.max_new_tokens;
+  for (int s : slots) room = std::min(room, d.max_new_tokens - e->h_suf_len[s]);
+  if (max_new < 1 || max_new > room) {
+    e->fail("max_new %d outside 1..%d (suffix KV capacity left)", max_new, room);
+    return ADVSPEC_ERR_INVALID;
+  }
+  if (!e->logits_broadcast && e->logits_slots != slots) {
+    e->fail("decode after decode_step must use the same opponents in the same order");
+    return ADVSPEC_ERR_STATE;
+  }
+  const int zero = 0;
+  for (int s : slots) {
+    E_CUDA(e, cudaMemcpyAsync(e->s_n_out + s, &zero, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    E_CUDA(e, cudaMemcpyAsync(e->s_done + s, &zero, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  }
+  E_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  // token 0 comes from the logits already on the device (the shared prefill's, or the last step's)
+  SampleParams sp0 = make_sample_params(e, temperature, eos_id, e->logits_broadcast, false, nullptr, true);
+  E_CUDA(e, launch_pdl(sample_kernel, dim3(n), dim3(1024), 0, e->stream, false, sp0));
+  e->launches++;
+
+  const int steps = max_new - 1;
+  const SampleParams sp = make_sample_params(e, temperature, eos_id, false, true, nullptr, true);
+  if (steps > 0) {
+    std::vector<int> key = slots;
+    key.push_back(-1);
+    key.push_back(e->prefix_len);
+    key.push_back(e->prefix_gen);
+    { int tbits; memcpy(&tbits, &temperature, sizeof tbits); key.push_back(tbits); }
+    key.push_back(eos_id);
+    const int64_t per_step = 7 * (int64_t)d.n_layers + 2;
+    if (e->use_graph) {
+      if (!e->graph || e->graph_key != key) {
+        if (e->graph) {
+          cudaGraphExecDestroy(e->graph);
+          e->graph = nullptr;
+        }
+        cudaGraph_t g = nullptr;
+        E_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        const int64_t before = e->launches;
+        advspec_status fs = enqueue_forward(e, n, nullptr);
+        cudaError_t le = launch_pdl(sample_kernel, dim3(n), dim3(1024), 0, e->stream, true, sp);
+        cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+        e->launches = before;  // capture only records; launches are counted per replay
+        if (fs != ADVSPEC_OK || le != cudaSuccess || ce != cudaSuccess) {
+          if (g) cudaGraphDestroy(g);
+          if (fs == ADVSPEC_OK)
+            e->fail("graph capture failed: %s", cudaGetErrorString(le != cudaSuccess ? le : ce));
+          return ADVSPEC_ERR_CUDA;
+        }
+        cudaError_t ie = cudaGraphInstantiate(&e->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) {
+          e->graph = nullptr;
+          e->fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+          return ADVSPEC_ERR_CUDA;
+        }
+        e->graph_key = key;
+      }
+    }
+    for (int s = 0; s < steps; ++s) {
+      if (e->use_graph) {
+        E_CUDA(e, cudaGraphLaunch(e->graph, e->stream));
+        e->launches += per_step;
+      } else {
+        advspec_status fs = enqueue_forward(e, n, nullptr);
+        if (fs != ADVSPEC_OK) return fs;
+        E_CUDA(e, launch_pdl(sample_kernel, dim3(n), dim3(1024), 0, e->stream, true, sp));
+        e->launches++;
+      }
+      if (eos_id >= 0 && (s % 32) == 31) {
+        int done_h[8];
+        E_CUDA(e, cudaMemcpyAsync(done_h, e->s_done, d.max_seqs * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        E_CUDA(e, cudaStreamSynchronize(e->stream));
+        bool all = true;
+        for (int sl : slots) all = all && done_h[sl] != 0;
+        if (all) {
+          e->tm.decode_steps = s + 1;
+          break;
+        }
+      }
+      e->tm.decode_steps = s + 1;
+    }
+  } else {
+    e->tm.decode_steps = 0;
+  }
+  E_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+  std::vector<int> h_out((size_t)d.max_seqs * d.max_new_tokens);
+  int n_out_h[8], suf_h[8];
+  E_CUDA(e, cudaMemcpyAsync(h_out.data(), e->s_out, h_out.size() * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  E_CUDA(e, cudaMemcpyAsync(n_out_h, e->s_n_out, d.max_seqs * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  E_CUDA(e, cudaMemcpyAsync(suf_h, e->s_suf_len, d.max_seqs * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  E_CUDA(e, cudaStreamSynchronize(e->stream));
+  E_CUDA(e, cudaEventElapsedTime(&e->tm.decode_ms, e->ev0, e->ev1));
+  e->tm.decode_batch = n;
+  st = check_watchdog(e);
+  if (st != ADVSPEC_OK) return st;
+  for (int i = 0; i < n; ++i) {
+    const int s = slots[i];
+    out_lens[i] = n_out_h[s];
+    e->h_suf_len[s] = suf_h[s];
+    for (int t = 0; t < max_new; ++t)
+      out_tokens[(size_t)i * max_new + t] = t < n_out_h[s] ? h_out[(size_t)s * d.max_new_tokens + t] : -1;
+  }
+  e->logits_broadcast = false;
+  e->logits_slots = slots;
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_decode_step(advspec_engine* e, const int32_t* seq_ids, int32_t n,
+                                   const int32_t* forced_tokens) {
+  if (!e || !forced_tokens) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  const auto& d = e->d;
+  E_CUDA(e, cudaSetDevice(e->device));
+  std::vector<int> slots;
+  advspec_status st = setup_batch(e, seq_ids, n, &slots);
+  if (st != ADVSPEC_OK) return st;
+  for (int i = 0; i < n; ++i) {
+    if (forced_tokens[i] < 0 || forced_tokens[i] >= d.vocab_size) {
+      e->fail("forced token %d outside the vocabulary", forced_tokens[i]);
+      return ADVSPEC_ERR_INVALID;
+    }
+    if (e->h_suf_len[slots[i]] >= d.max_new_tokens) {
+      e->fail("opponent %d has no suffix KV capacity left", slots[i]);
+      return ADVSPEC_ERR_INVALID;
+    }
+  }
+  E_CUDA(e, cudaMemcpyAsync(e->s_forced, forced_tokens, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  SampleParams sp = make_sample_params(e, 0.f, -1, false, false, e->s_forced, false);
+  E_CUDA(e, launch_pdl(sample_kernel, dim3(n), dim3(1024), 0, e->stream, false, sp));
+  e->launches++;
+  st = enqueue_forward(e, n, nullptr);
+  if (st != ADVSPEC_OK) return st;
+  advance_kernel<<<1, n, 0, e->stream>>>(e->s_slots, e->s_suf_len);
+  E_CUDA(e, cudaGetLastError());
+  E_CUDA(e, cudaStreamSynchronize(e->stream));
+  for (int s : slots) e->h_suf_len[s] += 1;
+  e->logits_broadcast = false;
+  e->logits_slots = slots;
+  return check_watchdog(e);
+}
+
+advspec_status advspec_get_logits(advspec_engine* e, int32_t n, float* out) {
+  if (!e || !out || n < 1) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  E_CUDA(e, cudaSetDevice(e->device));
+  const size_t V = e->d.vocab_size;
+  if (e->logits_broadcast) {
+    if (n != 1) {
+      e->fail("prefill logits have one row");
+      return ADVSPEC_ERR_INVALID;
+    }
+    E_CUDA(e, cudaMemcpy(out, e->prefill_logits, V * sizeof(float), cudaMemcpyDeviceToHost));
+  } else {
+    if (n > (int)e->logits_slots.size()) {
+      e->fail("only %zu logit rows are available", e->logits_slots.size());
+      return ADVSPEC_ERR_INVALID;
+    }
+    E_CUDA(e, cudaMemcpy(out, e->dlogits, (size_t)n * V * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_prefix_kv_region(advspec_engine* e, int32_t prefix_id, void** dev_ptr, size_t* bytes) {
+  if (!e || !dev_ptr || !bytes) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->prefix_gen == 0 || prefix_id != e->prefix_gen) {
+    e->fail("prefix %d is not live", prefix_id);
+    return ADVSPEC_ERR_STATE;
+  }
+  *dev_ptr = e->pkv;
+  *bytes = (size_t)e->d.n_layers * 2 * e->pkv_layer_elems * sizeof(__nv_bfloat16);
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_prefix_adopt(advspec_engine* e, int32_t n_tokens, const float* logits, int32_t* prefix_id) {
+  if (!e || !logits || !prefix_id) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (n_tokens < 1 || n_tokens > e->d.max_prefix_tokens) {
+    e->fail("adopted prefix of %d tokens outside 1..%d", n_tokens, e->d.max_prefix_tokens);
+    return ADVSPEC_ERR_INVALID;
+  }
+  E_CUDA(e, cudaSetDevice(e->device));
+  E_CUDA(e, cudaMemcpy(e->prefill_logits, logits, (size_t)e->d.vocab_size * sizeof(float), cudaMemcpyHostToDevice));
+  for (bool& u : e->slot_used) u = false;
+  static int next_gen = 1 << 20;
+  e->prefix_gen = next_gen++;
+  e->prefix_len = n_tokens;
+  e->logits_broadcast = true;
+  *prefix_id = e->prefix_gen;
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_get_timing(advspec_engine* e, advspec_timing* out) {
+  if (!e || !out) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->tm.kernel_launches = e->launches;
+  *out = e->tm;
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_profile_decode_step(advspec_engine* e, const int32_t* seq_ids, int32_t n) {
+  if (!e) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  E_CUDA(e, cudaSetDevice(e->device));
+  std::vector<int> slots;
+  advspec_status st = setup_batch(e, seq_ids, n, &slots);
+  if (st != ADVSPEC_OK) return st;
+  for (int s : slots)
+    if (e->h_suf_len[s] >= e->d.max_new_tokens) {
+      e->fail("opponent %d has no suffix KV capacity left for a profiled step", s);
+      return ADVSPEC_ERR_INVALID;
+    }
+  const size_t xb = (size_t)e->d.max_seqs * e->d.d_model * sizeof(float);
+  E_CUDA(e, cudaMemcpyAsync(e->dx_save, e->dx, xb, cudaMemcpyDeviceToDevice, e->stream));
+  // warm pass, then the timed pass (suffix length is not advanced: the same KV row is rewritten)
+  st = enqueue_forward(e, n, nullptr);
+  if (st != ADVSPEC_OK) return st;
+  E_CUDA(e, cudaMemcpyAsync(e->dx, e->dx_save, xb, cudaMemcpyDeviceToDevice, e->stream));
+  float ms = 0.f;
+  st = enqueue_forward(e, n, &ms);
+  if (st != ADVSPEC_OK) return st;
+  e->tm.gemv_ms = ms;
+  E_CUDA(e, cudaMemcpyAsync(e->dx, e->dx_save, xb, cudaMemcpyDeviceToDevice, e->stream));
+  E_CUDA(e, cudaStreamSynchronize(e->stream));
+  return check_watchdog(e);
+}
+
+advspec_status advspec_decode_step_bytes(advspec_engine* e, const int32_t* seq_ids, int32_t n,
+                                         double* step_bytes, double* gemv_bytes) {
+  if (!e || !seq_ids || !step_bytes || !gemv_bytes) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  const auto& d = e->d;
+  const double dm = d.d_model, QKV = qkv_dim(d), HD = (double)d.n_heads * d.head_dim;
+  // every matmul weight once, lm_head streamed, embedding table gathered (not streamed)
+  const double w = 2.0 * (d.n_layers * (QKV * dm + dm * HD + 2.0 * d.d_ff * dm + dm * d.d_ff) +
+                          (double)d.vocab_size * dm);
+  const double kvB = 2.0 * d.n_layers * d.n_kv_heads * d.head_dim * 2.0;
+  double toks = e->prefix_len;
+  for (int i = 0; i < n; ++i) {
+    const int s = seq_ids[i];
+    if (s < 0 || s >= d.max_seqs) return ADVSPEC_ERR_INVALID;
+    toks += e->h_suf_len[s];
+  }
+  *gemv_bytes = w;
+  *step_bytes = w + kvB * toks + kvB * n;
+  return ADVSPEC_OK;
+}
+
+// ------------------------------------------------------------- op-level
+static advspec_status op_begin(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    g_create_error = "no CUDA device for op-level call";
+    return ADVSPEC_ERR_CUDA;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return ADVSPEC_ERR_CUDA;
+  return ADVSPEC_OK;
+}
+static advspec_status op_end(const char* what) {
+  cudaError_t r = cudaDeviceSynchronize();
+  if (r != cudaSuccess) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(r);
+    return ADVSPEC_ERR_CUDA;
+  }
+  unsigned int code = 0;
+  cudaMemcpyFromSymbol(&code, g_watchdog_code, sizeof code);
+  if (code) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "%s: device watchdog tripped at site 0x%x", what, code & 0x7fffffffu);
+    g_create_error = buf;
+    unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_watchdog_code, &zero, sizeof zero);
+    return ADVSPEC_ERR_KERNEL;
+  }
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_op_gemm(int32_t device, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                               int64_t ldc, const void* aux, int32_t M, int32_t N, int32_t K, int32_t epilogue,
+                               int32_t act) {
+  advspec_status s = op_begin(device);
+  if (s) return s;
+  GemmParams p{C, ldc, reinterpret_cast<const float*>(aux), M, N, K, act};
+  std::string why;
+  cudaError_t r = launch_gemm(A, lda, M, B, ldb, p, epilogue, device, 0, &why);
+  if (r != cudaSuccess) {
+    g_create_error = std::string("op_gemm launch: ") + cudaGetErrorString(r) + " " + why;
+    return ADVSPEC_ERR_CUDA;
+  }
+  return op_end("op_gemm");
+}
+
+advspec_status advspec_op_gemm_check(int32_t device, const void* A, int64_t lda, const void* B, int64_t ldb,
+                                     void* C, int64_t ldc, const void* aux, int32_t M, int32_t N, int32_t K,
+                                     int32_t epilogue, int32_t act) {
+  advspec_status s = op_begin(device);
+  if (s) return s;
+  GemmParams p{C, ldc, reinterpret_cast<const float*>(aux), M, N, K, act};
+  cudaError_t r = launch_gemm_check(A, lda, B, ldb, p, epilogue, 0);
+  if (r != cudaSuccess) {
+    g_create_error = std::string("op_gemm_check launch: ") + cudaGetErrorString(r);
+    return ADVSPEC_ERR_CUDA;
+  }
+  return op_end("op_gemm_check");
+}
+
+advspec_status advspec_op_gemv(int32_t device, const void* W, const void* x, const void* norm_w,
+                               const void* bias, void* y, int32_t b, int32_t N, int32_t K, int32_t in_mode,
+                               int32_t epilogue, int32_t act, float eps) {
+  advspec_status s = op_begin(device);
+  if (s) return s;
+  if (b < 1 || b > 8 || (K % 8) || (epilogue == EPI_GATED_BF16 && (N % 2))) {
+    g_create_error = "op_gemv: need 1 <= b <= 8, K % 8 == 0, even N for the gated epilogue";
+    return ADVSPEC_ERR_INVALID;
+  }
+  GemvParams p{reinterpret_cast<const __nv_bfloat16*>(W), x, reinterpret_cast<const float*>(norm_w),
+               reinterpret_cast<const float*>(bias), y, N, K, in_mode, epilogue, act, eps};
+  cudaError_t r = launch_gemv(p, b, device, 0, false);
+  if (r != cudaSuccess) {
+    g_create_error = std::string("op_gemv launch: ") + cudaGetErrorString(r);
+    return ADVSPEC_ERR_CUDA;
+  }
+  return op_end("op_gemv");
+}
+
+advspec_status advspec_op_attn_prefill(int32_t device, const void* q, int64_t ldq, const void* kcache,
+                                       const void* vcache, int64_t kv_stride, void* out, int32_t n_q,
+                                       int32_t q_pos0, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
+                                       int32_t impl) {
+  advspec_status s = op_begin(device);
+  if (s) return s;
+  AttnPrefillParams p{reinterpret_cast<const __nv_bfloat16*>(q), ldq,
+                      reinterpret_cast<const __nv_bfloat16*>(kcache),
+                      reinterpret_cast<const __nv_bfloat16*>(vcache), kv_stride,
+                      reinterpret_cast<__nv_bfloat16*>(out), n_q, q_pos0, n_heads, n_kv_heads,
+                      1.0f / sqrtf((float)head_dim)};
+  cudaError_t r = launch_attn_prefill(p, head_dim, impl, 0, nullptr);
+  if (r != cudaSuccess) {
+    g_create_error = std::string("op_attn_prefill launch: ") + cudaGetErrorString(r);
+    return ADVSPEC_ERR_CUDA;
+  }
+  return op_end("op_attn_prefill");
+}
+
+}  // extern "C"
