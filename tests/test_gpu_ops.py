@@ -1,0 +1,144 @@
+"""Op-level parity of the sm_100a kernels through the C ABI (device pointers from torch)."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from advspec_b200 import engine as eng
+
+pytestmark = pytest.mark.gpu
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _err(lib):
+    return (lib.advspec_last_error(None) or b"").decode()
+
+
+def _act(x, act):
+    return torch.nn.functional.gelu(x, approximate="tanh") if act == 1 else torch.nn.functional.silu(x)
+
+
+def _gemm_ref(A, B, epi, act, bias, Cin):
+    acc = A.float() @ B.float().T
+    if epi == 0:
+        return (acc + (bias if bias is not None else 0)).bfloat16()
+    if epi == 1:
+        return Cin + acc
+    if epi == 2:
+        return (_act(acc[:, 0::2], act) * acc[:, 1::2]).bfloat16()
+    return acc
+
+
+GEMM_SHAPES = [(128, 256, 64), (256, 512, 512), (384, 768, 320), (200, 1000, 264), (70, 128, 128),
+               (1024, 6144, 4096)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_tcgen05(cuda_device, diag, M, N, K, epi):
+    lib = eng.load_library()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + epi)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) if epi == 0 else None
+    act = (M // 128) % 2
+    if epi in (1, 3):
+        Cbuf = torch.randn(M, N, device="cuda", generator=g)
+    elif epi == 2:
+        Cbuf = torch.zeros(M, N // 2, device="cuda", dtype=torch.bfloat16)
+    else:
+        Cbuf = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    ref = _gemm_ref(A, B, epi, act, bias, Cbuf.clone() if epi == 1 else None)
+    chk = Cbuf.clone()
+    st = lib.advspec_op_gemm(0, _ptr(A), K, _ptr(B), K, _ptr(Cbuf), Cbuf.shape[1], _ptr(bias), M, N, K, epi, act)
+    assert st == 0, _err(lib)
+    st = lib.advspec_op_gemm_check(0, _ptr(A), K, _ptr(B), K, _ptr(chk), chk.shape[1], _ptr(bias), M, N, K, epi, act)
+    assert st == 0, _err(lib)
+    scale = float(ref.float().abs().max()) + 1e-6
+    e_tc = float((Cbuf.float() - ref.float()).abs().max()) / scale
+    e_ck = float((chk.float() - ref.float()).abs().max()) / scale
+    diag[f"gemm/{M}x{N}x{K}/epi{epi}"] = {"tcgen05_rel_err": e_tc, "check_rel_err": e_ck}
+    # fp32 accumulate of bf16 products; outputs bf16-rounded for epi 0/2 (2^-8 relative)
+    tol = 1e-2 if epi in (0, 2) else 2e-3
+    assert e_ck < tol, f"check kernel off by {e_ck}"
+    assert e_tc < tol, f"tcgen05 kernel off by {e_tc} (check kernel {e_ck})"
+
+
+@pytest.mark.parametrize("N,K", [(512, 256), (6144, 4096), (4096, 14336), (1000, 3584), (2048, 18944)])
+@pytest.mark.parametrize("b", [1, 3, 5, 8])
+@pytest.mark.parametrize("mode", [(0, 0), (1, 0), (0, 1), (1, 2), (1, 3)])
+def test_gemv(cuda_device, diag, N, K, b, mode):
+    in_mode, epi = mode
+    lib = eng.load_library()
+    g = torch.Generator(device="cuda").manual_seed(N + K + b)
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    act, eps = 0, 1e-5
+    if in_mode == 0:
+        x = torch.randn(b, K, device="cuda", generator=g).bfloat16()
+        xin, nw = x.float(), None
+    else:
+        x = torch.randn(b, K, device="cuda", generator=g) * 3.0
+        nw = 1.0 + 0.1 * torch.randn(K, device="cuda", generator=g)
+        xin = (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * nw).bfloat16().float()
+    acc = xin @ W.float().T
+    bias = torch.randn(N, device="cuda", generator=g) if epi == 0 else None
+    if epi == 0:
+        y = torch.zeros(b, N, device="cuda", dtype=torch.bfloat16)
+        ref = (acc + bias).bfloat16()
+    elif epi == 1:
+        y = torch.randn(b, N, device="cuda", generator=g)
+        ref = y + acc
+    elif epi == 2:
+        y = torch.zeros(b, N // 2, device="cuda", dtype=torch.bfloat16)
+        ref = (_act(acc[:, 0::2], act) * acc[:, 1::2]).bfloat16()
+    else:
+        y = torch.zeros(b, N, device="cuda")
+        ref = acc
+    st = lib.advspec_op_gemv(0, _ptr(W), _ptr(x), _ptr(nw), _ptr(bias), _ptr(y), b, N, K, in_mode, epi, act,
+                             C.c_float(eps))
+    assert st == 0, _err(lib)
+    scale = float(ref.float().abs().max()) + 1e-6
+    e = float((y.float() - ref.float()).abs().max()) / scale
+    diag[f"gemv/{N}x{K}/b{b}/in{in_mode}/epi{epi}"] = e
+    assert e < (1e-2 if epi in (0, 2) else 2e-3), e
+
+
+def _attn_ref(q, kc, vc, n_q, q_pos0, H, Hkv, Dh):
+    # q [n_q, H*Dh(+...)] bf16; kc/vc [Hkv, stride, Dh]
+    total = q_pos0 + n_q
+    qh = q[:, : H * Dh].float().reshape(n_q, H, Dh)
+    k = kc[:, :total].float().repeat_interleave(H // Hkv, dim=0)  # [H, total, Dh]
+    v = vc[:, :total].float().repeat_interleave(H // Hkv, dim=0)
+    sc = torch.einsum("qhd,hkd->hqk", qh, k) / (Dh ** 0.5)
+    qpos = q_pos0 + torch.arange(n_q, device=q.device)
+    mask = torch.arange(total, device=q.device)[None, :] > qpos[:, None]
+    sc = sc.masked_fill(mask[None], float("-inf"))
+    return torch.einsum("hqk,hkd->qhd", sc.softmax(-1), v).reshape(n_q, H * Dh)
+
+
+@pytest.mark.parametrize("cfg", [(64, 0, 4, 2, 64), (200, 0, 4, 2, 128), (333, 100, 8, 2, 128),
+                                 (1024, 0, 8, 8, 128), (130, 62, 2, 1, 64), (96, 0, 2, 2, 256)])
+@pytest.mark.parametrize("impl", [0, 1])
+def test_attn_prefill(cuda_device, diag, cfg, impl):
+    n_q, q_pos0, H, Hkv, Dh = cfg
+    lib = eng.load_library()
+    g = torch.Generator(device="cuda").manual_seed(n_q + q_pos0 + H)
+    stride = q_pos0 + n_q + 37
+    ldq = (H + 2 * Hkv) * Dh
+    q = torch.randn(n_q, ldq, device="cuda", generator=g).bfloat16()
+    kc = torch.randn(Hkv, stride, Dh, device="cuda", generator=g).bfloat16()
+    vc = torch.randn(Hkv, stride, Dh, device="cuda", generator=g).bfloat16()
+    out = torch.zeros(n_q, H * Dh, device="cuda", dtype=torch.bfloat16)
+    st = lib.advspec_op_attn_prefill(0, _ptr(q), ldq, _ptr(kc), _ptr(vc), stride, _ptr(out), n_q, q_pos0, H,
+                                     Hkv, Dh, impl)
+    assert st == 0, _err(lib)
+    ref = _attn_ref(q, kc, vc, n_q, q_pos0, H, Hkv, Dh)
+    e = float((out.float() - ref).abs().max())
+    diag[f"attn_prefill/{cfg}/impl{impl}"] = e
+    # outputs are O(1); bf16 output rounding + bf16 P in the tensor-core kernel
+    assert e < 3e-2, e
