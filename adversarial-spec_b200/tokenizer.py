@@ -121,11 +121,15 @@ def generate_spec(tok: SyntheticTokenizer, n_tokens: int, seed: int, title: str 
         parts.append(piece)
         n += c
     text = "".join(parts)
-    while tok.count(text) < n_tokens:  # top up one single-token word at a time
-        text += " " + str(rng.choice(words))
-    ids = tok.encode(text)
-    assert len(ids) >= n_tokens
-    if len(ids) > n_tokens:
-        text = tok.decode(ids[:n_tokens])
-    # the reference strips stdin (debate.py:778): make the text strip-stable
+    for _ in range(4):
+        # the reference strips stdin (debate.py:778): keep the text strip-stable at exactly n tokens
+        text = text.strip()
+        c = tok.count(text)
+        if c == n_tokens:
+            break
+        if c > n_tokens:
+            text = tok.decode(tok.encode(text)[:n_tokens])
+        else:
+            text += "".join(" " + str(w) for w in rng.choice(words, size=n_tokens - c))
+    assert tok.count(text) == n_tokens and text == text.strip()
     return text

@@ -1,0 +1,85 @@
+"""The host mirror reproduces the UNMODIFIED reference CLI byte for byte on the golden cases
+(tests/golden/reference_cli_cases.json, produced by oracle/make_golden.py from
+/root/reference with a canned litellm stub)."""
+
+import io
+import json
+import sys
+import time
+from contextlib import redirect_stderr, redirect_stdout
+from pathlib import Path
+from types import SimpleNamespace
+from unittest.mock import patch
+
+import pytest
+
+from advspec_b200 import debate, models
+
+GOLDEN = Path(__file__).parent / "golden"
+CASES = json.loads((GOLDEN / "reference_cli_cases.json").read_text())
+
+
+def _canned(case):
+    def completion(**kw):
+        spec = case["responses"][kw["model"]]
+        time.sleep(spec.get("delay", 0.0))
+        if spec.get("raise"):
+            raise RuntimeError(spec["raise"])
+        usage = None if spec.get("no_usage") else SimpleNamespace(prompt_tokens=spec["in"],
+                                                                  completion_tokens=spec["out"])
+        return SimpleNamespace(choices=[SimpleNamespace(message=SimpleNamespace(content=spec["content"]))],
+                               usage=usage)
+    return completion
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_cli_matches_reference(case, monkeypatch, tmp_path):
+    monkeypatch.chdir(tmp_path)
+    for k in list(__import__("os").environ):
+        if k.endswith("_API_KEY"):
+            monkeypatch.delenv(k)
+    monkeypatch.setattr(sys, "argv", ["debate.py", *case["argv"]])
+    monkeypatch.setattr(sys, "stdin", io.StringIO(case["stdin"]))
+    monkeypatch.setattr(models, "cost_tracker", models.CostTracker())
+    monkeypatch.setattr(debate, "cost_tracker", models.cost_tracker)
+    out, err, rc = io.StringIO(), io.StringIO(), 0
+    with patch.object(models, "completion", _canned(case)), patch.object(models.time, "sleep", lambda s, _real=time.sleep: _real(0.2 * s)), \
+            redirect_stdout(out), redirect_stderr(err):
+        try:
+            debate.main()
+        except SystemExit as e:
+            rc = e.code or 0
+    exp = case["expected"]
+    assert rc == exp["returncode"]
+    assert out.getvalue() == exp["stdout"]
+    if case["name"] == "missing_key_exit2":
+        assert "gpt-4o (requires OPENAI_API_KEY)" in err.getvalue()
+    else:
+        assert err.getvalue() == exp["stderr"]
+
+
+def test_parsing_kats():
+    """[AGREE]/[SPEC] semantics (reference models.py:149-160; KATs of its test_models.py:161-190)."""
+    assert models.detect_agreement("fine\n[AGREE]\n")
+    assert not models.detect_agreement("agree")
+    assert models.extract_spec("a [SPEC]\n body \n[/SPEC] b") == "body"
+    assert models.extract_spec("[SPEC]only open") is None
+    assert models.extract_spec("only close[/SPEC]") is None
+    assert models.extract_spec("[SPEC]a[/SPEC][SPEC]b[/SPEC]") == "a"
+    assert models.extract_spec("[SPEC][/SPEC]") == ""
+
+
+def test_cost_tracker_math():
+    ct = models.CostTracker()
+    c = ct.add("gpt-4o", 1_000_000, 500_000)
+    assert c == pytest.approx(2.5 + 5.0)
+    c2 = ct.add("totally/unknown", 1000, 2000)  # $5/$15 default
+    assert c2 == pytest.approx(0.005 + 0.03)
+    assert ct.add("b200/llama-3-8b", 10**6, 10**6) == 0.0
+    assert ct.total_input_tokens == 2_001_000 and len(ct.by_model) == 3
+    assert "By model:" in ct.summary()
+
+
+def test_model_response_defaults():
+    r = models.ModelResponse(model="m", response="r", agreed=False, spec=None)
+    assert (r.error, r.input_tokens, r.output_tokens, r.cost) == (None, 0, 0, 0.0)
