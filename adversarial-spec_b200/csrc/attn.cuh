@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnDecodeParams p) {
     }
   }
 
+  const uint32_t gmask = 0xFFu << (lane & 24);
   for (int t = tb + grp; t < te; t += 16) {
     float kv[DPL];
     const uint2* ks = reinterpret_cast<const uint2*>(kb + (int64_t)t * DH + l8 * DPL);
@@ -352,9 +353,10 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnDecodeParams p) {
       float d = 0.f;
 #pragma unroll
       for (int e = 0; e < DPL; ++e) d = fmaf(q[r][e], kv[e], d);
-      d += __shfl_xor_sync(0xffffffffu, d, 1);
-      d += __shfl_xor_sync(0xffffffffu, d, 2);
-      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      // the 4 groups of a warp can run different trip counts: shuffle within the group only
+      d += __shfl_xor_sync(gmask, d, 1);
+      d += __shfl_xor_sync(gmask, d, 2);
+      d += __shfl_xor_sync(gmask, d, 4);
       sc[r] = d;  // already in log2 units
     }
     const uint2* vs = reinterpret_cast<const uint2*>(vb + (int64_t)t * DH + l8 * DPL);
@@ -383,6 +385,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnDecodeParams p) {
   }
 
   // merge the 4 groups of a warp (lanes l8, l8+8, l8+16, l8+24 hold the same dims)
+  __syncwarp();
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
 #pragma unroll

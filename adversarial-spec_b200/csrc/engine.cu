@@ -218,6 +218,16 @@ cudaError_t launch_gemm_check(const void* A, int64_t lda, const void* B, int64_t
 
 // ------------------------------------------------------------------- GEMV
 bool g_use_pdl = true;
+bool g_trace = false;
+// ADVSPEC_TRACE=1: synchronise after every decode-path launch and name it on stderr (debugging aid)
+#define ADV_TRACE(st, name)                                                      \
+  do {                                                                           \
+    if (g_trace) {                                                               \
+      cudaError_t _te = cudaStreamSynchronize(st);                               \
+      fprintf(stderr, "[advspec trace] %s -> %s\n", name, cudaGetErrorString(_te)); \
+      fflush(stderr);                                                            \
+    }                                                                            \
+  } while (0)
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -583,11 +593,13 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
     const LayerW w = layer_w(e, l);
     GemvParams g1{w.wqkv, e->dx, w.attn_norm, w.bqkv, e->dqkv, QKV, dm, 1, EPI_BF16, d.act, d.norm_eps};
     E_CUDA(e, gemv(g1));
+    ADV_TRACE(e->stream, "gemv qkv");
     E_CUDA(e, launch_pdl(rope_decode_kernel, dim3(b), dim3(256), 0, e->stream, true,
                          (const __nv_bfloat16*)e->dqkv, e->dq, suffix_k(e, l), suffix_v(e, l),
                          (int64_t)d.max_new_tokens, (const int*)e->s_slots, (const int*)e->s_suf_len,
                          e->prefix_len, (const float*)e->rope_cos, (const float*)e->rope_sin, d.n_heads,
                          d.n_kv_heads, d.head_dim));
+    ADV_TRACE(e->stream, "rope_decode");
     AttnDecodeParams ap{};
     ap.items = e->items;
     ap.q = e->dq;
@@ -606,20 +618,26 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
     ap.n_slots = e->n_slots;
     ap.scale = 1.0f / sqrtf((float)d.head_dim);
     E_CUDA(e, launch_attn_decode(ap, e->n_items, d.head_dim, e->stream, true));
+    ADV_TRACE(e->stream, "attn_decode");
     E_CUDA(e, launch_pdl(attn_decode_combine_kernel, dim3(b * d.n_heads), dim3(128), 0, e->stream, true,
                          (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o,
                          e->dattn, e->n_slots, d.head_dim));
+    ADV_TRACE(e->stream, "attn_combine");
     GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, EPI_RESADD_F32, d.act, d.norm_eps};
     E_CUDA(e, gemv(g2));
+    ADV_TRACE(e->stream, "gemv o");
     GemvParams g3{w.wgu, e->dx, w.mlp_norm, nullptr, e->dh, 2 * d.d_ff, dm, 1, EPI_GATED_BF16, d.act, d.norm_eps};
     E_CUDA(e, gemv(g3));
+    ADV_TRACE(e->stream, "gemv gate_up");
     GemvParams g4{w.wd, e->dh, nullptr, nullptr, e->dx, dm, d.d_ff, 0, EPI_RESADD_F32, d.act, d.norm_eps};
     E_CUDA(e, gemv(g4));
+    ADV_TRACE(e->stream, "gemv down");
     e->launches += 3;
   }
   GemvParams gl{lm_head_w(e), e->dx, final_norm_w(e), nullptr, e->dlogits, d.vocab_size, dm, 1, EPI_F32,
                 d.act, d.norm_eps};
   E_CUDA(e, gemv(gl));
+  ADV_TRACE(e->stream, "gemv lm_head");
   if (prof) {
     E_CUDA(e, cudaStreamSynchronize(e->stream));
     float total = 0.f;
@@ -760,6 +778,7 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   e->debug_flags = dbg ? atoi(dbg) : 0;
   e->use_graph = getenv("ADVSPEC_NO_GRAPH") == nullptr;
   g_use_pdl = getenv("ADVSPEC_NO_PDL") == nullptr;
+  g_trace = getenv("ADVSPEC_TRACE") != nullptr;
 
   auto boot = [&]() -> advspec_status {
     const auto& d = e->d;
@@ -1203,6 +1222,7 @@ advspec_status advspec_decode_step(advspec_engine* e, const int32_t* seq_ids, in
   E_CUDA(e, cudaMemcpyAsync(e->s_forced, forced_tokens, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
   SampleParams sp = make_sample_params(e, 0.f, -1, false, false, e->s_forced, false);
   E_CUDA(e, launch_pdl(sample_kernel, dim3(n), dim3(1024), 0, e->stream, false, sp));
+  ADV_TRACE(e->stream, "sample(forced)");
   e->launches++;
   st = enqueue_forward(e, n, nullptr);
   if (st != ADVSPEC_OK) return st;

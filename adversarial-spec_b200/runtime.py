@@ -200,3 +200,24 @@ def run_round(model_names: Sequence[str], system_prompt: str, user_message: str,
         with ThreadPoolExecutor(max_workers=len(plan)) as pool:
             list(pool.map(work, plan))
     return results
+
+
+def reduce_round_stats(max_values: Sequence[float], sum_values: Sequence[int], device: str = "cpu"):
+    """Multi-GPU bookkeeping of a round: times are the MAX over ranks, token/launch counts the SUM.
+    No data-path collective exists between panels; this is measurement only.
+    Works with any initialised torch.distributed backend (nccl on GPUs, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return list(max_values), list(sum_values)
+    m = torch.tensor(list(max_values), dtype=torch.float64, device=device)
+    s = torch.tensor(list(sum_values), dtype=torch.int64, device=device)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    return m.tolist(), s.tolist()
+
+
+def shard_panels(n_panels: int, rank: int, world: int) -> list[int]:
+    """Independent panels (or opponents of a heterogeneous panel) -> ranks, round-robin."""
+    return [i for i in range(n_panels) if i % world == rank]

@@ -294,13 +294,9 @@ def run_b200_arm(args, rank, world, local_rank):
         sys.stderr = real_stderr
 
     # max over ranks of the time, sum over ranks of the tokens
-    if world > 1:
-        t = torch.tensor([dev_ms, wall], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall = float(t[0]), float(t[1])
-        c = torch.tensor([out_tokens, launches], device="cuda", dtype=torch.int64)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        out_tokens, launches = int(c[0]), int(c[1])
+    (dev_ms, wall), (out_tokens, launches) = runtime.reduce_round_stats([dev_ms, wall], [out_tokens, launches],
+                                                                        device="cuda")
+    out_tokens, launches = int(out_tokens), int(launches)
 
     line = None
     if rank == 0:
