@@ -299,6 +299,7 @@ template <int DH>
 __global__ void __launch_bounds__(128) attn_decode_kernel(AttnDecodeParams p) {
   constexpr int DPL = DH / 8;  // dims per lane
   static_assert(DPL % 4 == 0, "head_dim must be a multiple of 32");
+  ktrace_mark(TK_ATTN);
   pdl_wait();
   const AttnItem it = p.items[blockIdx.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -444,6 +445,7 @@ __global__ void attn_decode_combine_kernel(const float* __restrict__ part_m,
                                            const float* __restrict__ part_l,
                                            const float* __restrict__ part_o,
                                            __nv_bfloat16* __restrict__ out, int n_slots, int DH) {
+  ktrace_mark(TK_COMBINE);
   pdl_wait();
   const int row = blockIdx.x;  // b*H + h
   float M = -INFINITY;

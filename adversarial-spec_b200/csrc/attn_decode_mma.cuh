@@ -1,0 +1,356 @@
+// attn_decode_mma.cuh — decode attention, second design: one kernel per layer does
+//   RoPE of the new q/k  ->  append k/v to the opponent's private suffix KV
+//   ->  split-KV flash-decoding on tensor cores (mma.sync m16n8k16, bf16)
+//   ->  log-sum-exp combine by the last split to finish (atomic ticket).
+// A work item is (KV head, opponent group, KV source): the shared prefix is cut
+// into splits that are read ONCE for all opponents and all query heads of the KV
+// head (up to 16 query rows = one MMA M tile); each opponent's suffix is its own
+// item.  K/V tiles of 64 keys stream through a cp.async ring; the 4 warps of a
+// CTA each take 16 keys of a tile and keep a private online-softmax state.
+// Replaces rope_decode_kernel + attn_decode_kernel + attn_decode_combine_kernel.
+#pragma once
+
+#include "attn.cuh"
+#include "common.cuh"
+
+namespace advspec {
+
+struct AttnItem2 {
+  int kv_head;
+  int seq;        // opponent slot whose suffix this item reads; -1: the shared prefix
+  int tok_begin;  // prefix slice [tok_begin, tok_end)
+  int tok_end;
+  int slot;       // partial slot written (prefix splits 0..n_splits-1, suffix = n_splits)
+  int group;      // ticket counter index: (kv_head, opponent group)
+  int expected;   // items that contribute to this group
+  int row_off;    // this item's rows = group rows [row_off, row_off + n_rows)
+  int n_rows;
+  int grp_n_rows;
+  unsigned char grp_b[16];     // batch index of each group row
+  unsigned char grp_head[16];  // query head of each group row
+};
+
+struct AttnDecode2Params {
+  const AttnItem2* items;
+  const __nv_bfloat16* qkv;  // [b][(H+2Hkv)*DH] raw projections of the new token (bias applied)
+  const float* rope_cos;     // [max_pos][DH/2]
+  const float* rope_sin;
+  const __nv_bfloat16* pk;   // prefix K [Hkv][pstride][DH]
+  const __nv_bfloat16* pv;
+  int64_t pstride;
+  __nv_bfloat16* sk;         // suffix K [max_seqs][Hkv][sstride][DH] (this layer)
+  __nv_bfloat16* sv;
+  int64_t sstride;
+  const int* slots;          // [b] batch index -> opponent slot
+  const int* suf_len;        // [max_seqs] suffix tokens already cached (before this step)
+  int prefix_len;
+  float* part_m;             // [b*H][n_slots]
+  float* part_l;
+  float* part_o;             // [b*H][n_slots][DH]
+  int* tickets;              // [groups], zero between launches
+  __nv_bfloat16* out;        // [b][H*DH]
+  int H, Hkv, n_slots;
+  float scale;
+};
+
+template <int DH, int NST>
+__global__ void __launch_bounds__(128) attn_decode_mma_kernel(AttnDecode2Params p) {
+  constexpr int BN = 64;
+  constexpr int CPR = DH / 8;
+  constexpr int TILE = BN * DH;  // elements of one K (or V) tile
+  extern __shared__ __align__(128) uint8_t ad_smem[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(ad_smem);  // [16][DH]
+  __nv_bfloat16* sKV = sQ + 16 * DH;                               // [NST][2][BN][DH]
+
+  // items and the prefix KV are constant for the whole decode call: read them before the dependency
+  ktrace_mark(TK_ATTN);
+  const AttnItem2 it = p.items[blockIdx.x];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int QKV = (p.H + 2 * p.Hkv) * DH;
+  constexpr int half = DH / 2;
+  auto swz = [](int row, int chunk) { return row * DH + ((chunk ^ (row & 7)) << 3); };
+
+  const __nv_bfloat16 *kb, *vb;
+  int tb, te;
+  if (it.seq < 0) {
+    kb = p.pk + (int64_t)it.kv_head * p.pstride * DH;
+    vb = p.pv + (int64_t)it.kv_head * p.pstride * DH;
+    tb = it.tok_begin;
+    te = it.tok_end;
+  } else {
+    pdl_wait();  // needs this step's projections and the suffix length
+    // append the new token's k (rotated) and v to this opponent's suffix, then attend over it
+    const int bi = it.grp_b[it.row_off];
+    const int t = p.suf_len[it.seq];
+    const int pos = p.prefix_len + t;
+    const int64_t base = ((int64_t)it.seq * p.Hkv + it.kv_head) * p.sstride * DH;
+    __nv_bfloat16* kdst = p.sk + base + (int64_t)t * DH;
+    __nv_bfloat16* vdst = p.sv + base + (int64_t)t * DH;
+    const __nv_bfloat16* ksrc = p.qkv + (int64_t)bi * QKV + (p.H + it.kv_head) * DH;
+    const __nv_bfloat16* vsrc = p.qkv + (int64_t)bi * QKV + (p.H + p.Hkv + it.kv_head) * DH;
+    for (int j = tid; j < half; j += 128) {
+      const float c = p.rope_cos[(int64_t)pos * half + j], s = p.rope_sin[(int64_t)pos * half + j];
+      const float a = __bfloat162float(ksrc[j]), bb = __bfloat162float(ksrc[j + half]);
+      kdst[j] = __float2bfloat16_rn(a * c - bb * s);
+      kdst[j + half] = __float2bfloat16_rn(bb * c + a * s);
+    }
+    for (int j = tid; j < DH; j += 128) vdst[j] = vsrc[j];
+    __threadfence_block();
+    kb = p.sk + base;
+    vb = p.sv + base;
+    tb = 0;
+    te = t + 1;
+  }
+
+  const int n_tiles = (te - tb + BN - 1) / BN;
+  auto load_tile = [&](int tile) {
+    const int st = tile % NST;
+    const int k0 = tb + tile * BN;
+    __nv_bfloat16* dK = sKV + (size_t)st * 2 * TILE;
+    __nv_bfloat16* dV = dK + TILE;
+    for (int id = tid; id < BN * CPR; id += 128) {
+      const int r = id / CPR, c = id % CPR;
+      const bool ok = (k0 + r) < te;
+      const int64_t off = (int64_t)(ok ? k0 + r : tb) * DH + c * 8;
+      cp_async16(dK + swz(r, c), kb + off, ok);
+      cp_async16(dV + swz(r, c), vb + off, ok);
+    }
+  };
+  // prefix K/V does not depend on this step's projections: get it moving before the dependency
+  if (it.seq < 0) {
+    for (int s = 0; s < NST - 1; ++s) {
+      if (s < n_tiles) load_tile(s);
+      cp_async_commit();
+    }
+    pdl_wait();
+  }
+
+  // stage the (rotated, bf16-rounded) query rows; rows past n_rows are zero
+  for (int i = tid; i < 16 * half; i += 128) {
+    const int r = i / half, j = i % half;
+    float r0 = 0.f, r1 = 0.f;
+    if (r < it.n_rows) {
+      const int bi = it.grp_b[it.row_off + r], head = it.grp_head[it.row_off + r];
+      const int pos = p.prefix_len + p.suf_len[p.slots[bi]];
+      const float c = p.rope_cos[(int64_t)pos * half + j], s = p.rope_sin[(int64_t)pos * half + j];
+      const __nv_bfloat16* qs = p.qkv + (int64_t)bi * QKV + head * DH;
+      const float a = __bfloat162float(qs[j]), bb = __bfloat162float(qs[j + half]);
+      r0 = a * c - bb * s;
+      r1 = bb * c + a * s;
+    }
+    const int c0 = j >> 3, c1 = (j + half) >> 3;
+    sQ[swz(r, c0) + (j & 7)] = __float2bfloat16_rn(r0);
+    sQ[swz(r, c1) + (j & 7)] = __float2bfloat16_rn(r1);
+  }
+  __syncthreads();  // sQ complete; the appended k/v row is visible to this CTA's loads
+
+  if (it.seq >= 0) {  // suffix tiles include the row appended above: load after the barrier
+    for (int s = 0; s < NST - 1; ++s) {
+      if (s < n_tiles) load_tile(s);
+      cp_async_commit();
+    }
+  }
+
+  uint32_t qf[DH / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < DH / 16; ++kk) {
+    const int mi = lane >> 3;
+    ldmatrix_x4(qf[kk], sQ + swz((lane & 7) + (mi & 1) * 8, kk * 2 + (mi >> 1)));
+  }
+  float o[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const float sl2 = p.scale * 1.4426950408889634f;
+
+  for (int j = 0; j < n_tiles; ++j) {
+    if (j + NST - 1 < n_tiles) load_tile(j + NST - 1);
+    cp_async_commit();
+    cp_async_wait<NST - 1>();
+    __syncthreads();
+    const __nv_bfloat16* bK = sKV + (size_t)(j % NST) * 2 * TILE;
+    const __nv_bfloat16* bV = bK + TILE;
+    const int kw0 = tb + j * BN + warp * 16;  // first key of this warp's 16-key slice
+    if (kw0 < te) {
+      float s[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < DH / 16; ++kk) {
+        uint32_t r[4];
+        const int mi = lane >> 3;
+        ldmatrix_x4(r, bK + swz(warp * 16 + (mi >> 1) * 8 + (lane & 7), kk * 2 + (mi & 1)));
+        mma_bf16_16816(s[0], qf[kk], r[0], r[1]);
+        mma_bf16_16816(s[1], qf[kk], r[2], r[3]);
+      }
+      if (kw0 + 16 > te) {
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          const int kp = kw0 + nb * 8 + 2 * t4;
+          if (kp >= te) s[nb][0] = s[nb][2] = -INFINITY;
+          if (kp + 1 >= te) s[nb][1] = s[nb][3] = -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float mx = fmaxf(fmaxf(s[0][2 * i], s[0][2 * i + 1]), fmaxf(s[1][2 * i], s[1][2 * i + 1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(m_run[i], mx);
+        const float m_off = (m_new == -INFINITY) ? 0.f : m_new * sl2;
+        const float corr = (m_run[i] == -INFINITY) ? 0.f : exp2f(m_run[i] * sl2 - m_off);
+        m_run[i] = m_new;
+        float rs = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          const float p0 = exp2f(s[nb][2 * i] * sl2 - m_off);
+          const float p1 = exp2f(s[nb][2 * i + 1] * sl2 - m_off);
+          s[nb][2 * i] = p0;
+          s[nb][2 * i + 1] = p1;
+          rs += p0 + p1;
+        }
+        l_run[i] = l_run[i] * corr + rs;
+        if (corr != 1.0f) {
+#pragma unroll
+          for (int d = 0; d < DH / 8; ++d) {
+            o[d][2 * i] *= corr;
+            o[d][2 * i + 1] *= corr;
+          }
+        }
+      }
+      uint32_t a[4];
+      a[0] = pack_bf16(s[0][0], s[0][1]);
+      a[1] = pack_bf16(s[0][2], s[0][3]);
+      a[2] = pack_bf16(s[1][0], s[1][1]);
+      a[3] = pack_bf16(s[1][2], s[1][3]);
+#pragma unroll
+      for (int db2 = 0; db2 < DH / 16; ++db2) {
+        uint32_t r[4];
+        const int mi = lane >> 3;
+        ldmatrix_x4_trans(r, bV + swz(warp * 16 + (mi & 1) * 8 + (lane & 7), db2 * 2 + (mi >> 1)));
+        mma_bf16_16816(o[2 * db2], a, r[0], r[1]);
+        mma_bf16_16816(o[2 * db2 + 1], a, r[2], r[3]);
+      }
+    }
+    __syncthreads();  // stage j % NST may be refilled by the next iteration's load
+  }
+  cp_async_wait<0>();
+
+  // ---- merge the 4 warps (disjoint key subsets) through shared memory (the ring is free now)
+  float* s_m = reinterpret_cast<float*>(sKV);  // [4][16]
+  float* s_l = s_m + 64;                        // [4][16]
+  float* s_o = s_l + 64;                        // [4][16][DH]
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float l = l_run[i];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    const int r = g + 8 * i;
+    if (t4 == 0) {
+      s_m[warp * 16 + r] = (m_run[i] == -INFINITY) ? -INFINITY : m_run[i] * sl2;
+      s_l[warp * 16 + r] = l;
+    }
+#pragma unroll
+    for (int d = 0; d < DH / 8; ++d) {
+      s_o[(warp * 16 + r) * DH + d * 8 + 2 * t4] = o[d][2 * i];
+      s_o[(warp * 16 + r) * DH + d * 8 + 2 * t4 + 1] = o[d][2 * i + 1];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < it.n_rows * DH; idx += 128) {
+    const int r = idx / DH, d = idx % DH;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, s_m[w * 16 + r]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = s_m[w * 16 + r];
+      const float c = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
+      L += s_l[w * 16 + r] * c;
+      O += s_o[(w * 16 + r) * DH + d] * c;
+    }
+    const int bi = it.grp_b[it.row_off + r], head = it.grp_head[it.row_off + r];
+    const int64_t ps = ((int64_t)bi * p.H + head) * p.n_slots + it.slot;
+    p.part_o[ps * DH + d] = O;
+    if (d == 0) {
+      p.part_m[ps] = M;
+      p.part_l[ps] = L;
+    }
+  }
+
+  pdl_launch_dependents();
+}
+
+// Merge of the split partials of one (opponent, query head) row per CTA: weights
+// 2^(m_s - M) / L are formed once in shared memory, then each thread owns one head
+// dimension and keeps 8 independent loads in flight over the slots.
+__global__ void __launch_bounds__(128) attn_decode_combine2_kernel(const float* __restrict__ part_m,
+                                                                   const float* __restrict__ part_l,
+                                                                   const float* __restrict__ part_o,
+                                                                   __nv_bfloat16* __restrict__ out,
+                                                                   int n_slots, int DH) {
+  __shared__ float w[320];
+  __shared__ float s_M, s_inv;
+  ktrace_mark(TK_COMBINE);
+  pdl_wait();
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int S = n_slots;
+  float lv[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int s = tid + i * 128;
+    if (s < 320) w[s] = (s < S) ? part_m[(int64_t)row * S + s] : -INFINITY;
+    lv[i] = (s < S) ? part_l[(int64_t)row * S + s] : 0.f;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float M = -INFINITY;
+    for (int s = tid; s < S; s += 32) M = fmaxf(M, w[s]);
+    M = warp_max(M);
+    if (tid == 0) s_M = M;
+  }
+  __syncthreads();
+  const float M = s_M;
+  float part = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int s = tid + i * 128;
+    if (s < S) {
+      const float ws = (w[s] == -INFINITY) ? 0.f : exp2f(w[s] - M);
+      part += lv[i] * ws;
+      w[s] = ws;
+    }
+  }
+  __shared__ float s_sum[4];
+  part = warp_sum(part);
+  if ((tid & 31) == 0) s_sum[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    const float L = s_sum[0] + s_sum[1] + s_sum[2] + s_sum[3];
+    s_inv = L > 0.f ? 1.0f / L : 0.f;
+  }
+  __syncthreads();
+  const float inv = s_inv;
+  for (int d = tid; d < DH; d += 128) {
+    const float* po = part_o + (int64_t)row * S * DH + d;
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    int s = 0;
+    for (; s + 8 <= S; s += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = po[(int64_t)(s + j) * DH];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = fmaf(v[j], w[s + j], a[j]);
+    }
+    for (; s < S; ++s) a[0] = fmaf(po[(int64_t)s * DH], w[s], a[0]);
+    const float tot = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    out[(int64_t)row * DH + d] = __float2bfloat16_rn(tot * inv);
+  }
+  pdl_launch_dependents();
+}
+
+}  // namespace advspec

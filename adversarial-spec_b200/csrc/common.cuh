@@ -70,6 +70,27 @@ __host__ __device__ __forceinline__ float uniform01(uint64_t seed, uint32_t step
 }
 
 // ---------------------------------------------------------------------------
+// In-situ kernel timeline: when enabled, block 0 of every decode-path kernel stamps
+// %globaltimer on entry.  Kernels of a step are serialised by data dependencies, so the
+// difference of consecutive stamps is each kernel's real cost (run time + launch gap)
+// inside the CUDA-graph replay — something neither ncu (serialised, cold cache) nor
+// host-side events (CPU-bound for 5 us kernels) can see.
+// ---------------------------------------------------------------------------
+constexpr int kTraceCap = 8192;
+__device__ unsigned long long g_ktrace[kTraceCap];
+__device__ unsigned int g_ktrace_n = 0;
+__device__ int g_ktrace_on = 0;
+enum TraceKind : int { TK_GEMV = 1, TK_ATTN = 2, TK_SAMPLE = 3, TK_ROPE = 4, TK_COMBINE = 5 };
+__device__ __forceinline__ void ktrace_mark(int kind) {
+  if (g_ktrace_on && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned int i = atomicAdd(&g_ktrace_n, 1u);
+    if (i < (unsigned int)kTraceCap) g_ktrace[i] = (t << 4) | (unsigned long long)kind;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // shared-memory addresses, mbarrier
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -232,4 +253,36 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+}  // namespace advspec
+
+namespace advspec {
+// 1-D bulk async copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// Sub-block barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads).
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// Reduce up to 32 independent values across the 32 lanes of a warp with 31 shuffles
+// (recursive halving); on return lane L holds the warp-wide sum of v[L].
+__device__ __forceinline__ float warp_reduce_32vals(float (&v)[32], int lane) {
+#pragma unroll
+  for (int n = 32, o = 16; o >= 1; n >>= 1, o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = upper ? v[i + n / 2] : v[i];
+      const float send = upper ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
 }  // namespace advspec

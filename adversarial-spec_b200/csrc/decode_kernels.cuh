@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(GemvParams p) {
   __shared__ float s_inv[B];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  ktrace_mark(TK_GEMV);
   // contiguous row range of this CTA, in units of 2 rows (gated pairs stay together)
   const int pairs = (p.N + 1) / 2;
   const int row_begin = (int)(((int64_t)pairs * blockIdx.x) / gridDim.x) * 2;
@@ -306,6 +307,7 @@ __global__ void rope_decode_kernel(const __nv_bfloat16* __restrict__ qkv, float*
                                    const int* __restrict__ suf_len, int prefix_len,
                                    const float* __restrict__ cs, const float* __restrict__ sn, int H,
                                    int Hkv, int DH) {
+  ktrace_mark(TK_ROPE);
   pdl_wait();
   const int b = blockIdx.x;
   const int slot = slots[b];
@@ -366,6 +368,7 @@ struct SampleParams {
 };
 
 __global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
+  ktrace_mark(TK_SAMPLE);
   pdl_wait();
   __shared__ float s_best[32];
   __shared__ int s_idx[32];

@@ -30,9 +30,12 @@
 #include <vector>
 
 #include "attn.cuh"
+#include "attn_decode_mma.cuh"
 #include "common.cuh"
 #include "decode_kernels.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemv_mma.cuh"
+#include "gemv_stream.cuh"
 
 using namespace advspec;
 
@@ -245,7 +248,9 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-cudaError_t launch_gemv(const GemvParams& p, int b, int device, cudaStream_t st, bool pdl) {
+int g_gemv_impl = 3;  // 3: bulk-async stream + tensor-core consumers (default); 2: same stream, CUDA-core consumers; 1: register loads (A/B only)
+
+cudaError_t launch_gemv_v1(const GemvParams& p, int b, int device, cudaStream_t st, bool pdl) {
   const int pairs = (p.N + 1) / 2;
   const int grid = std::max(1, std::min(2 * num_sms(device), pairs));
   dim3 g(grid), blk(kGemvThreads);
@@ -258,6 +263,100 @@ cudaError_t launch_gemv(const GemvParams& p, int b, int device, cudaStream_t st,
     case 6: return launch_pdl(gemv_kernel<6, 1>, g, blk, 0, st, pdl, p);
     case 7: return launch_pdl(gemv_kernel<7, 1>, g, blk, 0, st, pdl, p);
     case 8: return launch_pdl(gemv_kernel<8, 1>, g, blk, 0, st, pdl, p);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <int B>
+cudaError_t launch_gemv_stream_t(const GemvParams& p, int device, cudaStream_t st, bool pdl) {
+  constexpr int kMaxDyn = 220 * 1024;  // leaves room for the kernel's static shared memory
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = set_smem(gemv_stream_kernel<B>, kMaxDyn);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const size_t xbytes = (size_t)B * p.K * 2;
+  // the normalised activations (in_mode 1) always live in shared memory; plain bf16 inputs are
+  // copied there when they still leave a 3-stage ring, else read through L1 from global
+  int x_in_smem = 0;
+  size_t x_smem = 0;
+  if (p.in_mode == 1) {
+    x_smem = xbytes;
+  } else if (xbytes + 3 * (size_t)kGsStageBytes <= (size_t)kMaxDyn) {
+    x_in_smem = 1;
+    x_smem = xbytes;
+  }
+  x_smem = (x_smem + 127) / 128 * 128;
+  if (x_smem + 2 * (size_t)kGsStageBytes > (size_t)kMaxDyn) return cudaErrorInvalidValue;
+  int stages = (int)((kMaxDyn - x_smem) / kGsStageBytes);
+  stages = std::min(stages, kGsMaxStages);
+  const int pairs = (p.N + 1) / 2;
+  const int grid = std::max(1, std::min(num_sms(device), pairs));
+  const size_t dyn = (size_t)stages * kGsStageBytes + x_smem;
+  return launch_pdl(gemv_stream_kernel<B>, dim3(grid), dim3(kGsThreads), dyn, st, pdl, p, stages, x_in_smem);
+}
+
+template <int B>
+cudaError_t launch_gemv_mma_t(const GemvParams& p, int device, cudaStream_t st, bool pdl) {
+  constexpr int kMaxDyn = 216 * 1024;  // + 8.5 KB static = 224.5 KB of the 227 KB a CTA may use
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = set_smem(gemv_mma_kernel<B>, kMaxDyn);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const size_t xbytes = ((size_t)B * ((size_t)p.K * 2 + 16) + 127) / 128 * 128;
+  int x_in_smem = 0;
+  size_t x_smem = 0;
+  if (p.in_mode == 1) {
+    x_smem = xbytes;
+  } else if (xbytes + 4 * (size_t)kGmStageBytes <= (size_t)kMaxDyn) {
+    x_in_smem = 1;
+    x_smem = xbytes;
+  }
+  if (x_smem + 2 * (size_t)kGmStageBytes > (size_t)kMaxDyn) return cudaErrorInvalidValue;
+  const int stages = std::min<int>(kGmMaxStages, (int)((kMaxDyn - x_smem) / kGmStageBytes));
+  const int pairs = (p.N + 1) / 2;
+  const int grid = std::max(1, std::min(num_sms(device), pairs));
+  const size_t dyn = (size_t)stages * kGmStageBytes + x_smem;
+  return launch_pdl(gemv_mma_kernel<B>, dim3(grid), dim3(kGmThreads), dyn, st, pdl, p, stages, x_in_smem);
+}
+
+cudaError_t launch_gemv_mma(const GemvParams& p, int b, int device, cudaStream_t st, bool pdl) {
+  switch (b) {
+    case 1: return launch_gemv_mma_t<1>(p, device, st, pdl);
+    case 2: return launch_gemv_mma_t<2>(p, device, st, pdl);
+    case 3: return launch_gemv_mma_t<3>(p, device, st, pdl);
+    case 4: return launch_gemv_mma_t<4>(p, device, st, pdl);
+    case 5: return launch_gemv_mma_t<5>(p, device, st, pdl);
+    case 6: return launch_gemv_mma_t<6>(p, device, st, pdl);
+    case 7: return launch_gemv_mma_t<7>(p, device, st, pdl);
+    case 8: return launch_gemv_mma_t<8>(p, device, st, pdl);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_gemv(const GemvParams& p, int b, int device, cudaStream_t st, bool pdl) {
+  if (g_gemv_impl == 3) {
+    const bool ok3 = (p.K % 16 == 0) &&
+                     (p.in_mode != 1 || ((size_t)b * ((size_t)p.K * 2 + 16) + 2 * (size_t)kGmStageBytes + 256 <= (size_t)216 * 1024));
+    if (ok3) return launch_gemv_mma(p, b, device, st, pdl);
+    return launch_gemv_v1(p, b, device, st, pdl);
+  }
+  // fused-RMSNorm inputs live in shared memory next to the ring; shapes that cannot keep at least a
+  // 2-stage ring (no model in the table: K = d_model there) take the register-load kernel
+  const bool fits = p.in_mode != 1 || ((size_t)b * p.K * 2 + 2 * (size_t)kGsStageBytes + 256 <= (size_t)220 * 1024);
+  if (g_gemv_impl == 1 || !fits) return launch_gemv_v1(p, b, device, st, pdl);
+  switch (b) {
+    case 1: return launch_gemv_stream_t<1>(p, device, st, pdl);
+    case 2: return launch_gemv_stream_t<2>(p, device, st, pdl);
+    case 3: return launch_gemv_stream_t<3>(p, device, st, pdl);
+    case 4: return launch_gemv_stream_t<4>(p, device, st, pdl);
+    case 5: return launch_gemv_stream_t<5>(p, device, st, pdl);
+    case 6: return launch_gemv_stream_t<6>(p, device, st, pdl);
+    case 7: return launch_gemv_stream_t<7>(p, device, st, pdl);
+    case 8: return launch_gemv_stream_t<8>(p, device, st, pdl);
   }
   return cudaErrorInvalidValue;
 }
@@ -306,6 +405,34 @@ cudaError_t launch_attn_decode(const AttnDecodeParams& p, int n_items, int DH, c
   return cudaErrorInvalidValue;
 }
 
+int g_attn_impl = 2;  // 2: fused tensor-core decode attention (default); 1: scalar 3-kernel path (A/B, other head dims)
+
+cudaError_t launch_attn_decode2(const AttnDecode2Params& p, int n_items, int DH, cudaStream_t st, bool pdl) {
+  constexpr int NST = 3;
+  dim3 g(n_items), blk(128);
+  if (DH == 128) {
+    static bool done = false;
+    const int smem = 16 * 128 * 2 + NST * 2 * 64 * 128 * 2;
+    if (!done) {
+      cudaError_t e = set_smem(attn_decode_mma_kernel<128, NST>, smem);
+      if (e != cudaSuccess) return e;
+      done = true;
+    }
+    return launch_pdl(attn_decode_mma_kernel<128, NST>, g, blk, smem, st, pdl, p);
+  }
+  if (DH == 64) {
+    static bool done = false;
+    const int smem = 16 * 64 * 2 + NST * 2 * 64 * 64 * 2;
+    if (!done) {
+      cudaError_t e = set_smem(attn_decode_mma_kernel<64, NST>, smem);
+      if (e != cudaSuccess) return e;
+      done = true;
+    }
+    return launch_pdl(attn_decode_mma_kernel<64, NST>, g, blk, smem, st, pdl, p);
+  }
+  return cudaErrorInvalidValue;
+}
+
 __global__ void advance_kernel(const int* slots, int* suf_len) {
   pdl_wait();
   suf_len[slots[threadIdx.x]] += 1;
@@ -349,6 +476,10 @@ struct advspec_engine {
   float *part_m = nullptr, *part_l = nullptr, *part_o = nullptr;
   AttnItem* items = nullptr;
   int items_cap = 0, n_items = 0, n_slots = 0;
+  AttnItem2* items2 = nullptr;  // fused tensor-core decode attention
+  int items2_cap = 0, n_items2 = 0;
+  int* tickets = nullptr;
+  bool attn_fused = false;  // this engine's shape is served by attn_decode_mma_kernel
 
   // opponent state (device arrays indexed by slot)
   int *s_slots = nullptr, *s_forced = nullptr;  // [max_seqs] batch -> slot / forced tokens
@@ -507,7 +638,7 @@ void free_all(advspec_engine* e) {
   if (e->graph) cudaGraphExecDestroy(e->graph);
   void* ptrs[] = {e->w, e->inv_freq, e->rope_cos, e->rope_sin, e->pkv, e->skv, e->p_tokens, e->p_x,
                   e->p_xn, e->p_qkv, e->p_attn, e->p_h, e->prefill_logits, e->dx, e->dx_save, e->dq,
-                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->items,
+                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->items, e->items2, e->tickets,
                   e->s_slots, e->s_forced, e->s_seeds, e->s_suf_len, e->s_n_out, e->s_done,
                   e->s_cur_tok, e->s_out};
   for (void* p : ptrs)
@@ -568,6 +699,59 @@ void build_items(advspec_engine* e, const std::vector<int>& slots, std::vector<A
   }
 }
 
+// Work items of the fused decode attention: per KV head, opponents are grouped so that a group's
+// query rows (opponents x G heads) fill one 16-row MMA tile; the prefix is cut into splits shared by
+// the whole group, each opponent's suffix is its own item; the group's last finisher combines.
+void build_items2(advspec_engine* e, const std::vector<int>& slots, std::vector<AttnItem2>* out, int* n_slots) {
+  const auto& d = e->d;
+  const int b = (int)slots.size();
+  const int G = d.n_heads / d.n_kv_heads;
+  const int opg = std::max(1, 16 / G);  // opponents per group
+  const int n_og = (b + opg - 1) / opg;
+  const int groups = d.n_kv_heads * n_og;
+  // one wave: 2 CTAs per SM are resident; suffix items take b * Hkv of those slots
+  const int slots_left = std::max(groups, 2 * num_sms(e->device) - b * d.n_kv_heads);
+  int n_splits = std::max(1, slots_left / std::max(1, groups));
+  n_splits = std::min(n_splits, std::max(1, e->prefix_len / 256));
+  n_splits = std::min(n_splits, 300);
+  *n_slots = n_splits + 1;
+  out->clear();
+  for (int hk = 0; hk < d.n_kv_heads; ++hk) {
+    for (int og = 0; og < n_og; ++og) {
+      AttnItem2 base{};
+      base.kv_head = hk;
+      base.group = hk * n_og + og;
+      const int o0 = og * opg, o1 = std::min(b, o0 + opg);
+      base.expected = n_splits + (o1 - o0);
+      base.grp_n_rows = 0;
+      for (int bi = o0; bi < o1; ++bi)
+        for (int g = 0; g < G; ++g) {
+          base.grp_b[base.grp_n_rows] = (unsigned char)bi;
+          base.grp_head[base.grp_n_rows] = (unsigned char)(hk * G + g);
+          base.grp_n_rows++;
+        }
+      for (int s = 0; s < n_splits; ++s) {
+        AttnItem2 it = base;
+        it.seq = -1;
+        it.tok_begin = (int)((int64_t)e->prefix_len * s / n_splits);
+        it.tok_end = (int)((int64_t)e->prefix_len * (s + 1) / n_splits);
+        it.slot = s;
+        it.row_off = 0;
+        it.n_rows = base.grp_n_rows;
+        out->push_back(it);
+      }
+      for (int bi = o0; bi < o1; ++bi) {
+        AttnItem2 it = base;
+        it.seq = slots[bi];
+        it.slot = n_splits;
+        it.row_off = (bi - o0) * G;
+        it.n_rows = G;
+        out->push_back(it);
+      }
+    }
+  }
+}
+
 // Enqueue one forward step (all layers + lm_head) for the batch in s_slots.
 advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
   const auto& d = e->d;
@@ -594,35 +778,68 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
     GemvParams g1{w.wqkv, e->dx, w.attn_norm, w.bqkv, e->dqkv, QKV, dm, 1, EPI_BF16, d.act, d.norm_eps};
     E_CUDA(e, gemv(g1));
     ADV_TRACE(e->stream, "gemv qkv");
+    if (e->attn_fused) {
+      AttnDecode2Params a2{};
+      a2.items = e->items2;
+      a2.qkv = e->dqkv;
+      a2.rope_cos = e->rope_cos;
+      a2.rope_sin = e->rope_sin;
+      a2.pk = prefix_k(e, l);
+      a2.pv = prefix_v(e, l);
+      a2.pstride = d.max_prefix_tokens;
+      a2.sk = suffix_k(e, l);
+      a2.sv = suffix_v(e, l);
+      a2.sstride = d.max_new_tokens;
+      a2.slots = e->s_slots;
+      a2.suf_len = e->s_suf_len;
+      a2.prefix_len = e->prefix_len;
+      a2.part_m = e->part_m;
+      a2.part_l = e->part_l;
+      a2.part_o = e->part_o;
+      a2.tickets = e->tickets;
+      a2.out = e->dattn;
+      a2.H = d.n_heads;
+      a2.Hkv = d.n_kv_heads;
+      a2.n_slots = e->n_slots;
+      a2.scale = 1.0f / sqrtf((float)d.head_dim);
+      E_CUDA(e, launch_attn_decode2(a2, e->n_items2, d.head_dim, e->stream, true));
+      ADV_TRACE(e->stream, "attn_decode_mma");
+      E_CUDA(e, launch_pdl(attn_decode_combine2_kernel, dim3(b * d.n_heads), dim3(128), 0, e->stream, true,
+                           (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o, e->dattn,
+                           e->n_slots, d.head_dim));
+      ADV_TRACE(e->stream, "attn_combine2");
+      e->launches -= 1;  // two kernels instead of rope + attention + combine (counted as 3 below)
+    } else {
     E_CUDA(e, launch_pdl(rope_decode_kernel, dim3(b), dim3(256), 0, e->stream, true,
-                         (const __nv_bfloat16*)e->dqkv, e->dq, suffix_k(e, l), suffix_v(e, l),
-                         (int64_t)d.max_new_tokens, (const int*)e->s_slots, (const int*)e->s_suf_len,
-                         e->prefix_len, (const float*)e->rope_cos, (const float*)e->rope_sin, d.n_heads,
-                         d.n_kv_heads, d.head_dim));
-    ADV_TRACE(e->stream, "rope_decode");
-    AttnDecodeParams ap{};
-    ap.items = e->items;
-    ap.q = e->dq;
-    ap.pk = prefix_k(e, l);
-    ap.pv = prefix_v(e, l);
-    ap.pstride = d.max_prefix_tokens;
-    ap.sk = suffix_k(e, l);
-    ap.sv = suffix_v(e, l);
-    ap.sstride = d.max_new_tokens;
-    ap.suf_len = e->s_suf_len;
-    ap.part_m = e->part_m;
-    ap.part_l = e->part_l;
-    ap.part_o = e->part_o;
-    ap.H = d.n_heads;
-    ap.Hkv = d.n_kv_heads;
-    ap.n_slots = e->n_slots;
-    ap.scale = 1.0f / sqrtf((float)d.head_dim);
-    E_CUDA(e, launch_attn_decode(ap, e->n_items, d.head_dim, e->stream, true));
-    ADV_TRACE(e->stream, "attn_decode");
-    E_CUDA(e, launch_pdl(attn_decode_combine_kernel, dim3(b * d.n_heads), dim3(128), 0, e->stream, true,
-                         (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o,
-                         e->dattn, e->n_slots, d.head_dim));
-    ADV_TRACE(e->stream, "attn_combine");
+                           (const __nv_bfloat16*)e->dqkv, e->dq, suffix_k(e, l), suffix_v(e, l),
+                           (int64_t)d.max_new_tokens, (const int*)e->s_slots, (const int*)e->s_suf_len,
+                           e->prefix_len, (const float*)e->rope_cos, (const float*)e->rope_sin, d.n_heads,
+                           d.n_kv_heads, d.head_dim));
+      ADV_TRACE(e->stream, "rope_decode");
+      AttnDecodeParams ap{};
+      ap.items = e->items;
+      ap.q = e->dq;
+      ap.pk = prefix_k(e, l);
+      ap.pv = prefix_v(e, l);
+      ap.pstride = d.max_prefix_tokens;
+      ap.sk = suffix_k(e, l);
+      ap.sv = suffix_v(e, l);
+      ap.sstride = d.max_new_tokens;
+      ap.suf_len = e->s_suf_len;
+      ap.part_m = e->part_m;
+      ap.part_l = e->part_l;
+      ap.part_o = e->part_o;
+      ap.H = d.n_heads;
+      ap.Hkv = d.n_kv_heads;
+      ap.n_slots = e->n_slots;
+      ap.scale = 1.0f / sqrtf((float)d.head_dim);
+      E_CUDA(e, launch_attn_decode(ap, e->n_items, d.head_dim, e->stream, true));
+      ADV_TRACE(e->stream, "attn_decode");
+      E_CUDA(e, launch_pdl(attn_decode_combine_kernel, dim3(b * d.n_heads), dim3(128), 0, e->stream, true,
+                           (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o,
+                           e->dattn, e->n_slots, d.head_dim));
+      ADV_TRACE(e->stream, "attn_combine");
+    }
     GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, EPI_RESADD_F32, d.act, d.norm_eps};
     E_CUDA(e, gemv(g2));
     ADV_TRACE(e->stream, "gemv o");
@@ -712,6 +929,17 @@ advspec_status setup_batch(advspec_engine* e, const int32_t* seq_ids, int n, std
   e->n_items = (int)items.size();
   E_CUDA(e, cudaMemcpyAsync(e->items, items.data(), items.size() * sizeof(AttnItem), cudaMemcpyHostToDevice,
                             e->stream));
+  std::vector<AttnItem2> items2;
+  if (e->attn_fused) {
+    build_items2(e, *slots, &items2, &e->n_slots);
+    if ((int)items2.size() > e->items2_cap) {
+      e->fail("internal: %zu fused attention items exceed capacity %d", items2.size(), e->items2_cap);
+      return ADVSPEC_ERR_INVALID;
+    }
+    e->n_items2 = (int)items2.size();
+    E_CUDA(e, cudaMemcpyAsync(e->items2, items2.data(), items2.size() * sizeof(AttnItem2), cudaMemcpyHostToDevice,
+                              e->stream));
+  }
   E_CUDA(e, cudaStreamSynchronize(e->stream));  // items/slots vectors die with this scope
   return ADVSPEC_OK;
 }
@@ -779,6 +1007,8 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   e->use_graph = getenv("ADVSPEC_NO_GRAPH") == nullptr;
   g_use_pdl = getenv("ADVSPEC_NO_PDL") == nullptr;
   g_trace = getenv("ADVSPEC_TRACE") != nullptr;
+  if (const char* gi = getenv("ADVSPEC_GEMV_IMPL")) g_gemv_impl = std::max(1, std::min(3, atoi(gi)));
+  if (const char* ai = getenv("ADVSPEC_ATTN_IMPL")) g_attn_impl = atoi(ai) == 1 ? 1 : 2;
 
   auto boot = [&]() -> advspec_status {
     const auto& d = e->d;
@@ -823,6 +1053,11 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, dmalloc(&e->part_o, B * d.n_heads * (size_t)(max_splits + 1) * d.head_dim));
     e->items_cap = d.n_kv_heads * (((int)B * G + 3) / 4) * max_splits + (int)B * d.n_kv_heads * ((G + 3) / 4);
     E_CUDA(e, dmalloc(&e->items, (size_t)e->items_cap));
+    e->items2_cap = d.n_kv_heads * (int)B * (max_splits + 16);
+    E_CUDA(e, dmalloc(&e->items2, (size_t)e->items2_cap));
+    E_CUDA(e, dmalloc(&e->tickets, (size_t)d.n_kv_heads * B));
+    E_CUDA(e, cudaMemsetAsync(e->tickets, 0, (size_t)d.n_kv_heads * B * sizeof(int), e->stream));
+    e->attn_fused = g_attn_impl == 2 && (d.head_dim == 64 || d.head_dim == 128) && G <= 16 && d.n_heads <= 255;
     E_CUDA(e, dmalloc(&e->s_slots, B));
     E_CUDA(e, dmalloc(&e->s_forced, B));
     E_CUDA(e, dmalloc(&e->s_seeds, B));
@@ -1121,7 +1356,7 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
     key.push_back(e->prefix_gen);
     { int tbits; memcpy(&tbits, &temperature, sizeof tbits); key.push_back(tbits); }
     key.push_back(eos_id);
-    const int64_t per_step = 7 * (int64_t)d.n_layers + 2;
+    const int64_t per_step = (e->attn_fused ? 6 : 7) * (int64_t)d.n_layers + 2;
     if (e->use_graph) {
       if (!e->graph || e->graph_key != key) {
         if (e->graph) {
@@ -1342,6 +1577,33 @@ advspec_status advspec_decode_step_bytes(advspec_engine* e, const int32_t* seq_i
   return ADVSPEC_OK;
 }
 
+advspec_status advspec_ktrace_enable(advspec_engine* e, int32_t on) {
+  if (!e) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  E_CUDA(e, cudaSetDevice(e->device));
+  E_CUDA(e, cudaStreamSynchronize(e->stream));
+  const int v = on ? 1 : 0;
+  const unsigned int zero = 0;
+  E_CUDA(e, cudaMemcpyToSymbol(g_ktrace_on, &v, sizeof v));
+  E_CUDA(e, cudaMemcpyToSymbol(g_ktrace_n, &zero, sizeof zero));
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_ktrace_read(advspec_engine* e, uint64_t* out, int32_t cap, int32_t* n) {
+  if (!e || !out || !n || cap < 0) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  E_CUDA(e, cudaSetDevice(e->device));
+  E_CUDA(e, cudaStreamSynchronize(e->stream));
+  unsigned int cnt = 0;
+  E_CUDA(e, cudaMemcpyFromSymbol(&cnt, g_ktrace_n, sizeof cnt));
+  const int m = (int)std::min<unsigned int>(std::min<unsigned int>(cnt, (unsigned int)kTraceCap), (unsigned int)cap);
+  if (m > 0) E_CUDA(e, cudaMemcpyFromSymbol(out, g_ktrace, (size_t)m * sizeof(uint64_t)));
+  const unsigned int zero = 0;
+  E_CUDA(e, cudaMemcpyToSymbol(g_ktrace_n, &zero, sizeof zero));
+  *n = m;
+  return ADVSPEC_OK;
+}
+
 // ------------------------------------------------------------- op-level
 static advspec_status op_begin(int device) {
   int ndev = 0;
@@ -1411,6 +1673,8 @@ advspec_status advspec_op_gemv(int32_t device, const void* W, const void* x, con
   }
   GemvParams p{reinterpret_cast<const __nv_bfloat16*>(W), x, reinterpret_cast<const float*>(norm_w),
                reinterpret_cast<const float*>(bias), y, N, K, in_mode, epilogue, act, eps};
+  if (const char* gi = getenv("ADVSPEC_GEMV_IMPL")) g_gemv_impl = std::max(1, std::min(3, atoi(gi)));
+  if (const char* ai = getenv("ADVSPEC_ATTN_IMPL")) g_attn_impl = atoi(ai) == 1 ? 1 : 2;
   cudaError_t r = launch_gemv(p, b, device, 0, false);
   if (r != cudaSuccess) {
     g_create_error = std::string("op_gemv launch: ") + cudaGetErrorString(r);

@@ -190,6 +190,15 @@ advspec_status advspec_decode_step_bytes(advspec_engine *e,
                                          double *step_bytes,
                                          double *gemv_bytes);
 
+/* In-situ kernel timeline of the decode path.  While enabled, block 0 of every decode
+ * kernel stamps the GPU's global nanosecond timer on entry; consecutive stamps give each
+ * kernel's real cost (run + launch gap) inside the CUDA-graph replay.  `advspec_ktrace_read`
+ * copies up to cap entries ((ns << 4) | kind; kind 1 = weight-streaming GEMV, 2 = attention,
+ * 3 = sampler, 4 = RoPE/append, 5 = combine) and resets the log. */
+advspec_status advspec_ktrace_enable(advspec_engine *e, int32_t on);
+advspec_status advspec_ktrace_read(advspec_engine *e, uint64_t *out, int32_t cap,
+                                   int32_t *n);
+
 /* ---- op-level entry points (device pointers; used by tests/) ------------- */
 
 /* C[M,N] = A[M,K] * B[N,K]^T on tcgen05; epilogue: 0 = bf16 store (+bias f32[N]
