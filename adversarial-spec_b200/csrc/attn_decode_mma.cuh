@@ -15,23 +15,10 @@
 
 namespace advspec {
 
-struct AttnItem2 {
-  int kv_head;
-  int seq;        // opponent slot whose suffix this item reads; -1: the shared prefix
-  int tok_begin;  // prefix slice [tok_begin, tok_end)
-  int tok_end;
-  int slot;       // partial slot written (prefix splits 0..n_splits-1, suffix = n_splits)
-  int group;      // ticket counter index: (kv_head, opponent group)
-  int expected;   // items that contribute to this group
-  int row_off;    // this item's rows = group rows [row_off, row_off + n_rows)
-  int n_rows;
-  int grp_n_rows;
-  unsigned char grp_b[16];     // batch index of each group row
-  unsigned char grp_head[16];  // query head of each group row
-};
-
+// Work decomposition is pure arithmetic on blockIdx (no table to fetch): per KV head, opponents are
+// grouped so that a group's query rows (opponents x G heads) fill one 16-row MMA tile; the prefix is
+// cut into n_splits slices shared by the whole group; each opponent's suffix is its own item.
 struct AttnDecode2Params {
-  const AttnItem2* items;
   const __nv_bfloat16* qkv;  // [b][(H+2Hkv)*DH] raw projections of the new token (bias applied)
   const float* rope_cos;     // [max_pos][DH/2]
   const float* rope_sin;
@@ -41,20 +28,19 @@ struct AttnDecode2Params {
   __nv_bfloat16* sk;         // suffix K [max_seqs][Hkv][sstride][DH] (this layer)
   __nv_bfloat16* sv;
   int64_t sstride;
-  const int* slots;          // [b] batch index -> opponent slot
-  const int* suf_len;        // [max_seqs] suffix tokens already cached (before this step)
+  const int* pos_b;          // [b] absolute position of each opponent's new token (device state)
+  int slots[8];              // batch index -> opponent slot (fixed for the decode call)
   int prefix_len;
   float* part_m;             // [b*H][n_slots]
   float* part_l;
   float* part_o;             // [b*H][n_slots][DH]
-  int* tickets;              // [groups], zero between launches
-  __nv_bfloat16* out;        // [b][H*DH]
-  int H, Hkv, n_slots;
+  int b, H, Hkv, G;
+  int opg, n_og, n_splits, n_slots;  // opponents per group, groups per KV head, prefix splits, n_splits+1
   float scale;
 };
 
 template <int DH, int NST>
-__global__ void __launch_bounds__(128) attn_decode_mma_kernel(AttnDecode2Params p) {
+__global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Params p) {
   constexpr int BN = 64;
   constexpr int CPR = DH / 8;
   constexpr int TILE = BN * DH;  // elements of one K (or V) tile
@@ -62,40 +48,53 @@ __global__ void __launch_bounds__(128) attn_decode_mma_kernel(AttnDecode2Params 
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(ad_smem);  // [16][DH]
   __nv_bfloat16* sKV = sQ + 16 * DH;                               // [NST][2][BN][DH]
 
-  // items and the prefix KV are constant for the whole decode call: read them before the dependency
   ktrace_mark(TK_ATTN);
-  const AttnItem2 it = p.items[blockIdx.x];
+  phase_mark(0);
+  if (!g_ktrace_on) pdl_launch_dependents();  // dependents only pre-stage weights before their own wait
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = warp >> 2, w4 = warp & 3;  // two warp groups take alternate key tiles
   const int g = lane >> 2, t4 = lane & 3;
   const int QKV = (p.H + 2 * p.Hkv) * DH;
   constexpr int half = DH / 2;
   auto swz = [](int row, int chunk) { return row * DH + ((chunk ^ (row & 7)) << 3); };
 
+  // ---- which item am I
+  const int per_group = p.n_splits + p.opg;
+  const int grp = blockIdx.x / per_group, j = blockIdx.x % per_group;
+  const int hk = grp / p.n_og, og = grp % p.n_og;
+  const int o0 = og * p.opg;
+  const int n_opp = min(p.opg, p.b - o0);
+  const bool is_prefix = j < p.n_splits;
+  if (!is_prefix && (j - p.n_splits) >= n_opp) return;  // padding item of a short last group
+  const int row_off = is_prefix ? 0 : (j - p.n_splits) * p.G;  // rows inside the group's 16-row tile
+  const int n_rows = is_prefix ? n_opp * p.G : p.G;
+  const int slot_out = is_prefix ? j : p.n_splits;
+
   const __nv_bfloat16 *kb, *vb;
   int tb, te;
-  if (it.seq < 0) {
-    kb = p.pk + (int64_t)it.kv_head * p.pstride * DH;
-    vb = p.pv + (int64_t)it.kv_head * p.pstride * DH;
-    tb = it.tok_begin;
-    te = it.tok_end;
+  if (is_prefix) {
+    kb = p.pk + (int64_t)hk * p.pstride * DH;
+    vb = p.pv + (int64_t)hk * p.pstride * DH;
+    tb = (int)((int64_t)p.prefix_len * j / p.n_splits);
+    te = (int)((int64_t)p.prefix_len * (j + 1) / p.n_splits);
   } else {
-    pdl_wait();  // needs this step's projections and the suffix length
+    pdl_wait();  // needs this step's projections and positions
     // append the new token's k (rotated) and v to this opponent's suffix, then attend over it
-    const int bi = it.grp_b[it.row_off];
-    const int t = p.suf_len[it.seq];
-    const int pos = p.prefix_len + t;
-    const int64_t base = ((int64_t)it.seq * p.Hkv + it.kv_head) * p.sstride * DH;
+    const int bi = o0 + (j - p.n_splits);
+    const int pos = p.pos_b[bi];
+    const int t = pos - p.prefix_len;
+    const int64_t base = ((int64_t)p.slots[bi] * p.Hkv + hk) * p.sstride * DH;
     __nv_bfloat16* kdst = p.sk + base + (int64_t)t * DH;
     __nv_bfloat16* vdst = p.sv + base + (int64_t)t * DH;
-    const __nv_bfloat16* ksrc = p.qkv + (int64_t)bi * QKV + (p.H + it.kv_head) * DH;
-    const __nv_bfloat16* vsrc = p.qkv + (int64_t)bi * QKV + (p.H + p.Hkv + it.kv_head) * DH;
-    for (int j = tid; j < half; j += 128) {
-      const float c = p.rope_cos[(int64_t)pos * half + j], s = p.rope_sin[(int64_t)pos * half + j];
-      const float a = __bfloat162float(ksrc[j]), bb = __bfloat162float(ksrc[j + half]);
-      kdst[j] = __float2bfloat16_rn(a * c - bb * s);
-      kdst[j + half] = __float2bfloat16_rn(bb * c + a * s);
+    const __nv_bfloat16* ksrc = p.qkv + (int64_t)bi * QKV + (p.H + hk) * DH;
+    const __nv_bfloat16* vsrc = p.qkv + (int64_t)bi * QKV + (p.H + p.Hkv + hk) * DH;
+    for (int jj = tid; jj < half; jj += 256) {
+      const float c = p.rope_cos[(int64_t)pos * half + jj], s = p.rope_sin[(int64_t)pos * half + jj];
+      const float a = __bfloat162float(ksrc[jj]), bb = __bfloat162float(ksrc[jj + half]);
+      kdst[jj] = __float2bfloat16_rn(a * c - bb * s);
+      kdst[jj + half] = __float2bfloat16_rn(bb * c + a * s);
     }
-    for (int j = tid; j < DH; j += 128) vdst[j] = vsrc[j];
+    for (int jj = tid; jj < DH; jj += 256) vdst[jj] = vsrc[jj];
     __threadfence_block();
     kb = p.sk + base;
     vb = p.sv + base;
@@ -109,7 +108,7 @@ __global__ void __launch_bounds__(128) attn_decode_mma_kernel(AttnDecode2Params 
     const int k0 = tb + tile * BN;
     __nv_bfloat16* dK = sKV + (size_t)st * 2 * TILE;
     __nv_bfloat16* dV = dK + TILE;
-    for (int id = tid; id < BN * CPR; id += 128) {
+    for (int id = tid; id < BN * CPR; id += 256) {
       const int r = id / CPR, c = id % CPR;
       const bool ok = (k0 + r) < te;
       const int64_t off = (int64_t)(ok ? k0 + r : tb) * DH + c * 8;
@@ -117,40 +116,58 @@ __global__ void __launch_bounds__(128) attn_decode_mma_kernel(AttnDecode2Params 
       cp_async16(dV + swz(r, c), vb + off, ok);
     }
   };
-  // prefix K/V does not depend on this step's projections: get it moving before the dependency
-  if (it.seq < 0) {
-    for (int s = 0; s < NST - 1; ++s) {
+  // Put the whole slice in flight at once when it fits the ring (prefix KV is constant during decode,
+  // so this happens before the dependency wait)
+  if (is_prefix) {
+    for (int s = 0; s < NST; ++s) {
       if (s < n_tiles) load_tile(s);
       cp_async_commit();
     }
+    phase_mark(1);
     pdl_wait();
+    phase_mark(2);
   }
 
-  // stage the (rotated, bf16-rounded) query rows; rows past n_rows are zero
-  for (int i = tid; i < 16 * half; i += 128) {
-    const int r = i / half, j = i % half;
-    float r0 = 0.f, r1 = 0.f;
-    if (r < it.n_rows) {
-      const int bi = it.grp_b[it.row_off + r], head = it.grp_head[it.row_off + r];
-      const int pos = p.prefix_len + p.suf_len[p.slots[bi]];
-      const float c = p.rope_cos[(int64_t)pos * half + j], s = p.rope_sin[(int64_t)pos * half + j];
-      const __nv_bfloat16* qs = p.qkv + (int64_t)bi * QKV + head * DH;
-      const float a = __bfloat162float(qs[j]), bb = __bfloat162float(qs[j + half]);
-      r0 = a * c - bb * s;
-      r1 = bb * c + a * s;
+  // ---- stage the rotated, bf16-rounded query rows (rows past n_rows are zero): one thread handles
+  // 8 consecutive rotation pairs of one row with 16-byte loads and stores
+  for (int i = tid; i < 16 * (half / 8); i += 256) {
+    const int r = i / (half / 8), jc = i % (half / 8);  // row, chunk of 8 pairs
+    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+    if (r < n_rows) {
+      const int gr = row_off + r;
+      const int bi = o0 + gr / p.G, head = hk * p.G + gr % p.G;
+      const int pos = p.pos_b[bi];
+      const __nv_bfloat16* qs = p.qkv + (int64_t)bi * QKV + head * DH + jc * 8;
+      const uint4 a4 = *reinterpret_cast<const uint4*>(qs);
+      const uint4 b4 = *reinterpret_cast<const uint4*>(qs + half);
+      const float4 c0 = *reinterpret_cast<const float4*>(p.rope_cos + (int64_t)pos * half + jc * 8);
+      const float4 c1 = *reinterpret_cast<const float4*>(p.rope_cos + (int64_t)pos * half + jc * 8 + 4);
+      const float4 s0 = *reinterpret_cast<const float4*>(p.rope_sin + (int64_t)pos * half + jc * 8);
+      const float4 s1 = *reinterpret_cast<const float4*>(p.rope_sin + (int64_t)pos * half + jc * 8 + 4);
+      const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
+      uint32_t lo_w[4], hi_w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a0 = bf16lo(aw[e]), a1 = bf16hi(aw[e]), b0 = bf16lo(bw[e]), b1 = bf16hi(bw[e]);
+        lo_w[e] = pack_bf16(a0 * cs[2 * e] - b0 * sn[2 * e], a1 * cs[2 * e + 1] - b1 * sn[2 * e + 1]);
+        hi_w[e] = pack_bf16(b0 * cs[2 * e] + a0 * sn[2 * e], b1 * cs[2 * e + 1] + a1 * sn[2 * e + 1]);
+      }
+      lo = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+      hi = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
     }
-    const int c0 = j >> 3, c1 = (j + half) >> 3;
-    sQ[swz(r, c0) + (j & 7)] = __float2bfloat16_rn(r0);
-    sQ[swz(r, c1) + (j & 7)] = __float2bfloat16_rn(r1);
+    *reinterpret_cast<uint4*>(sQ + swz(r, jc)) = lo;
+    *reinterpret_cast<uint4*>(sQ + swz(r, jc + half / 8)) = hi;
   }
   __syncthreads();  // sQ complete; the appended k/v row is visible to this CTA's loads
-
-  if (it.seq >= 0) {  // suffix tiles include the row appended above: load after the barrier
-    for (int s = 0; s < NST - 1; ++s) {
+  if (!is_prefix) {
+    for (int s = 0; s < NST; ++s) {
       if (s < n_tiles) load_tile(s);
       cp_async_commit();
     }
   }
+  phase_mark(3);
 
   uint32_t qf[DH / 16][4];
 #pragma unroll
@@ -164,83 +181,91 @@ __global__ void __launch_bounds__(128) attn_decode_mma_kernel(AttnDecode2Params 
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const float sl2 = p.scale * 1.4426950408889634f;
 
-  for (int j = 0; j < n_tiles; ++j) {
-    if (j + NST - 1 < n_tiles) load_tile(j + NST - 1);
-    cp_async_commit();
+  for (int jt = 0; jt < n_tiles; ++jt) {
+    // tiles 0..NST-1 were issued up front; tile jt >= NST was issued at iteration jt - NST + 1
     cp_async_wait<NST - 1>();
     __syncthreads();
-    const __nv_bfloat16* bK = sKV + (size_t)(j % NST) * 2 * TILE;
-    const __nv_bfloat16* bV = bK + TILE;
-    const int kw0 = tb + j * BN + warp * 16;  // first key of this warp's 16-key slice
-    if (kw0 < te) {
-      float s[2][4];
+    if ((jt & 1) == wg) {
+      const __nv_bfloat16* bK = sKV + (size_t)(jt % NST) * 2 * TILE;
+      const __nv_bfloat16* bV = bK + TILE;
+      const int kw0 = tb + jt * BN + w4 * 16;  // first key of this warp's 16-key slice
+      if (kw0 < te) {
+        float s[2][4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+        for (int i = 0; i < 2; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
 #pragma unroll
-      for (int kk = 0; kk < DH / 16; ++kk) {
-        uint32_t r[4];
-        const int mi = lane >> 3;
-        ldmatrix_x4(r, bK + swz(warp * 16 + (mi >> 1) * 8 + (lane & 7), kk * 2 + (mi & 1)));
-        mma_bf16_16816(s[0], qf[kk], r[0], r[1]);
-        mma_bf16_16816(s[1], qf[kk], r[2], r[3]);
-      }
-      if (kw0 + 16 > te) {
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-          const int kp = kw0 + nb * 8 + 2 * t4;
-          if (kp >= te) s[nb][0] = s[nb][2] = -INFINITY;
-          if (kp + 1 >= te) s[nb][1] = s[nb][3] = -INFINITY;
+        for (int kk = 0; kk < DH / 16; ++kk) {
+          uint32_t r[4];
+          const int mi = lane >> 3;
+          ldmatrix_x4(r, bK + swz(w4 * 16 + (mi >> 1) * 8 + (lane & 7), kk * 2 + (mi & 1)));
+          mma_bf16_16816(s[0], qf[kk], r[0], r[1]);
+          mma_bf16_16816(s[1], qf[kk], r[2], r[3]);
         }
-      }
+        if (kw0 + 16 > te) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float mx = fmaxf(fmaxf(s[0][2 * i], s[0][2 * i + 1]), fmaxf(s[1][2 * i], s[1][2 * i + 1]));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float m_new = fmaxf(m_run[i], mx);
-        const float m_off = (m_new == -INFINITY) ? 0.f : m_new * sl2;
-        const float corr = (m_run[i] == -INFINITY) ? 0.f : exp2f(m_run[i] * sl2 - m_off);
-        m_run[i] = m_new;
-        float rs = 0.f;
-#pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
-          const float p0 = exp2f(s[nb][2 * i] * sl2 - m_off);
-          const float p1 = exp2f(s[nb][2 * i + 1] * sl2 - m_off);
-          s[nb][2 * i] = p0;
-          s[nb][2 * i + 1] = p1;
-          rs += p0 + p1;
-        }
-        l_run[i] = l_run[i] * corr + rs;
-        if (corr != 1.0f) {
-#pragma unroll
-          for (int d = 0; d < DH / 8; ++d) {
-            o[d][2 * i] *= corr;
-            o[d][2 * i + 1] *= corr;
+          for (int nb = 0; nb < 2; ++nb) {
+            const int kp = kw0 + nb * 8 + 2 * t4;
+            if (kp >= te) s[nb][0] = s[nb][2] = -INFINITY;
+            if (kp + 1 >= te) s[nb][1] = s[nb][3] = -INFINITY;
           }
         }
-      }
-      uint32_t a[4];
-      a[0] = pack_bf16(s[0][0], s[0][1]);
-      a[1] = pack_bf16(s[0][2], s[0][3]);
-      a[2] = pack_bf16(s[1][0], s[1][1]);
-      a[3] = pack_bf16(s[1][2], s[1][3]);
 #pragma unroll
-      for (int db2 = 0; db2 < DH / 16; ++db2) {
-        uint32_t r[4];
-        const int mi = lane >> 3;
-        ldmatrix_x4_trans(r, bV + swz(warp * 16 + (mi & 1) * 8 + (lane & 7), db2 * 2 + (mi >> 1)));
-        mma_bf16_16816(o[2 * db2], a, r[0], r[1]);
-        mma_bf16_16816(o[2 * db2 + 1], a, r[2], r[3]);
+        for (int i = 0; i < 2; ++i) {
+          float mx = fmaxf(fmaxf(s[0][2 * i], s[0][2 * i + 1]), fmaxf(s[1][2 * i], s[1][2 * i + 1]));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          const float m_new = fmaxf(m_run[i], mx);
+          const float m_off = (m_new == -INFINITY) ? 0.f : m_new * sl2;
+          const float corr = (m_run[i] == -INFINITY) ? 0.f : exp2f(m_run[i] * sl2 - m_off);
+          m_run[i] = m_new;
+          float rs = 0.f;
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) {
+            const float p0 = exp2f(s[nb][2 * i] * sl2 - m_off);
+            const float p1 = exp2f(s[nb][2 * i + 1] * sl2 - m_off);
+            s[nb][2 * i] = p0;
+            s[nb][2 * i + 1] = p1;
+            rs += p0 + p1;
+          }
+          l_run[i] = l_run[i] * corr + rs;
+          if (corr != 1.0f) {
+#pragma unroll
+            for (int d = 0; d < DH / 8; ++d) {
+              o[d][2 * i] *= corr;
+              o[d][2 * i + 1] *= corr;
+            }
+          }
+        }
+        uint32_t a[4];
+        a[0] = pack_bf16(s[0][0], s[0][1]);
+        a[1] = pack_bf16(s[0][2], s[0][3]);
+        a[2] = pack_bf16(s[1][0], s[1][1]);
+        a[3] = pack_bf16(s[1][2], s[1][3]);
+#pragma unroll
+        for (int db2 = 0; db2 < DH / 16; ++db2) {
+          uint32_t r[4];
+          const int mi = lane >> 3;
+          ldmatrix_x4_trans(r, bV + swz(w4 * 16 + (mi & 1) * 8 + (lane & 7), db2 * 2 + (mi >> 1)));
+          mma_bf16_16816(o[2 * db2], a, r[0], r[1]);
+          mma_bf16_16816(o[2 * db2 + 1], a, r[2], r[3]);
+        }
       }
     }
-    __syncthreads();  // stage j % NST may be refilled by the next iteration's load
+    if (jt + NST < n_tiles) {
+      __syncthreads();  // stage jt % NST is free again
+      load_tile(jt + NST);
+    }
+    cp_async_commit();
   }
   cp_async_wait<0>();
+  __syncthreads();  // every warp is done with the ring before it is reused for the merge
+  phase_mark(4);
 
-  // ---- merge the 4 warps (disjoint key subsets) through shared memory (the ring is free now)
-  float* s_m = reinterpret_cast<float*>(sKV);  // [4][16]
-  float* s_l = s_m + 64;                        // [4][16]
-  float* s_o = s_l + 64;                        // [4][16][DH]
+  // ---- merge the 8 warps (disjoint key subsets) through shared memory
+  constexpr int OP = DH + 8;                    // padded row pitch (floats): 2-way instead of 8-way conflicts
+  float* s_m = reinterpret_cast<float*>(sKV);  // [8][16]
+  float* s_l = s_m + 128;                       // [8][16]
+  float* s_o = s_l + 128;                       // [8][16][OP]
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     float l = l_run[i];
@@ -253,33 +278,33 @@ __global__ void __launch_bounds__(128) attn_decode_mma_kernel(AttnDecode2Params 
     }
 #pragma unroll
     for (int d = 0; d < DH / 8; ++d) {
-      s_o[(warp * 16 + r) * DH + d * 8 + 2 * t4] = o[d][2 * i];
-      s_o[(warp * 16 + r) * DH + d * 8 + 2 * t4 + 1] = o[d][2 * i + 1];
+      *reinterpret_cast<float2*>(&s_o[(warp * 16 + r) * OP + d * 8 + 2 * t4]) = make_float2(o[d][2 * i], o[d][2 * i + 1]);
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < it.n_rows * DH; idx += 128) {
+  for (int idx = tid; idx < n_rows * DH; idx += 256) {
     const int r = idx / DH, d = idx % DH;
     float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) M = fmaxf(M, s_m[w * 16 + r]);
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, s_m[w * 16 + r]);
     float L = 0.f, O = 0.f;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
+    for (int w = 0; w < 8; ++w) {
       const float mw = s_m[w * 16 + r];
       const float c = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
       L += s_l[w * 16 + r] * c;
-      O += s_o[(w * 16 + r) * DH + d] * c;
+      O += s_o[(w * 16 + r) * OP + d] * c;
     }
-    const int bi = it.grp_b[it.row_off + r], head = it.grp_head[it.row_off + r];
-    const int64_t ps = ((int64_t)bi * p.H + head) * p.n_slots + it.slot;
+    const int gr = row_off + r;
+    const int bi = o0 + gr / p.G, head = hk * p.G + gr % p.G;
+    const int64_t ps = ((int64_t)bi * p.H + head) * p.n_slots + slot_out;
     p.part_o[ps * DH + d] = O;
     if (d == 0) {
       p.part_m[ps] = M;
       p.part_l[ps] = L;
     }
   }
-
+  phase_mark(5);
   pdl_launch_dependents();
 }
 
@@ -294,6 +319,7 @@ __global__ void __launch_bounds__(128) attn_decode_combine2_kernel(const float* 
   __shared__ float w[320];
   __shared__ float s_M, s_inv;
   ktrace_mark(TK_COMBINE);
+  if (!g_ktrace_on) pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x, tid = threadIdx.x;
   const int S = n_slots;

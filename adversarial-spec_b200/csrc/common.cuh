@@ -80,13 +80,25 @@ constexpr int kTraceCap = 8192;
 __device__ unsigned long long g_ktrace[kTraceCap];
 __device__ unsigned int g_ktrace_n = 0;
 __device__ int g_ktrace_on = 0;
-enum TraceKind : int { TK_GEMV = 1, TK_ATTN = 2, TK_SAMPLE = 3, TK_ROPE = 4, TK_COMBINE = 5 };
+enum TraceKind : int { TK_GEMV = 1, TK_ATTN = 2, TK_SAMPLE = 3, TK_ROPE = 4, TK_COMBINE = 5, TK_SAMPLE_SCAN = 6 };
 __device__ __forceinline__ void ktrace_mark(int kind) {
-  if (g_ktrace_on && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (g_ktrace_on && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     const unsigned int i = atomicAdd(&g_ktrace_n, 1u);
     if (i < (unsigned int)kTraceCap) g_ktrace[i] = (t << 4) | (unsigned long long)kind;
+  }
+}
+
+// Phase stamps of ONE CTA (blockIdx.x == g_phase_cta) of the most recent launch of an instrumented
+// kernel: where inside the kernel the time goes (diagnostic; only written while tracing is on).
+__device__ unsigned long long g_phase[16];
+__device__ int g_phase_cta = 1;
+__device__ __forceinline__ void phase_mark(int i) {
+  if (g_ktrace_on && blockIdx.x == (unsigned)g_phase_cta && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_phase[i] = t;
   }
 }
 

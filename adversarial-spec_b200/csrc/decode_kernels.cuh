@@ -359,6 +359,10 @@ struct SampleParams {
   int out_stride;
   int eos_id;
   int advance;               // 1: the KV of the previous input token is now in the cache
+  int* pos_b;                // [b] absolute position of each opponent's next input token
+  int prefix_len;
+  const float* part_best;    // [b][kSampleChunks] from sample_partial_kernel, or null: scan here
+  const int* part_idx;
   const int* forced;         // teacher forcing: [b] tokens to use instead of sampling
   int* cur_tok;              // [max_seqs] next input token
   const __nv_bfloat16* embed;
@@ -367,8 +371,52 @@ struct SampleParams {
   float embed_scale;
 };
 
+// Stage 1 of sampling: grid (chunks, b); every CTA scans a slice of the vocabulary and leaves its best
+// (perturbed score, index) in part_best / part_idx [b][chunks].  sample_kernel then only merges those.
+constexpr int kSampleChunks = 64;
+__global__ void __launch_bounds__(256) sample_partial_kernel(SampleParams p, float* __restrict__ part_best,
+                                                             int* __restrict__ part_idx) {
+  ktrace_mark(TK_SAMPLE_SCAN);
+  if (!g_ktrace_on) pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float s_best[8];
+  __shared__ int s_idx[8];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int slot = p.slots[b];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t step = (uint32_t)p.n_out[slot];
+  const float* lg = p.logits + (p.broadcast_logits ? 0 : (int64_t)b * p.V);
+  const uint64_t seed = p.seeds[slot];
+  const float invT = p.temperature > 0.f ? 1.0f / p.temperature : 1.0f;
+  const int per = (p.V + kSampleChunks - 1) / kSampleChunks;
+  const int v0 = chunk * per, v1 = min(p.V, v0 + per);
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  for (int v = v0 + tid; v < v1; v += 256) {
+    float sc = lg[v] * invT;
+    if (p.temperature > 0.f) sc -= logf(-logf(uniform01(seed, step, (uint32_t)v)));
+    if (sc > best || (sc == best && v < bidx)) { best = sc; bidx = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+  }
+  if (lane == 0) { s_best[warp] = best; s_idx[warp] = bidx; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (s_best[w] > best || (s_best[w] == best && s_idx[w] < bidx)) { best = s_best[w]; bidx = s_idx[w]; }
+    part_best[b * kSampleChunks + chunk] = best;
+    part_idx[b * kSampleChunks + chunk] = bidx;
+  }
+  pdl_launch_dependents();
+}
+
 __global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
   ktrace_mark(TK_SAMPLE);
+  if (!g_ktrace_on) pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_best[32];
   __shared__ int s_idx[32];
@@ -376,11 +424,33 @@ __global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
   const int b = blockIdx.x;
   const int slot = p.slots[b];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (p.advance && tid == 0) p.suf_len[slot] += 1;  // previous token's KV is in place
+  if (tid == 0) {
+    int sl = p.suf_len[slot];
+    if (p.advance) p.suf_len[slot] = ++sl;  // previous token's KV is in place
+    p.pos_b[b] = p.prefix_len + sl;         // absolute position of the token about to be fed
+  }
   const uint32_t step = (uint32_t)p.n_out[slot];
   const bool was_done = p.done[slot] != 0;
 
-  if (p.forced == nullptr) {
+  if (p.forced == nullptr && p.part_best != nullptr) {
+    // merge the per-chunk winners of sample_partial_kernel (same tie rule: lowest index)
+    if (warp == 0) {
+      float best = -INFINITY;
+      int bidx = 0x7fffffff;
+      for (int c = lane; c < kSampleChunks; c += 32) {
+        const float ob = p.part_best[b * kSampleChunks + c];
+        const int oi = p.part_idx[b * kSampleChunks + c];
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+      }
+      if (lane == 0) s_tok = bidx;
+    }
+  } else if (p.forced == nullptr) {
     const float* lg = p.logits + (p.broadcast_logits ? 0 : (int64_t)b * p.V);
     const uint64_t seed = p.seeds[slot];
     float best = -INFINITY;

@@ -297,9 +297,12 @@ cudaError_t launch_gemv_stream_t(const GemvParams& p, int device, cudaStream_t s
   return launch_pdl(gemv_stream_kernel<B>, dim3(grid), dim3(kGsThreads), dyn, st, pdl, p, stages, x_in_smem);
 }
 
+int g_attn_min_split = 256;  // ADVSPEC_ATTN_MIN_SPLIT: fewest prefix tokens worth a split of their own
+size_t g_x_smem_max = 40000;  // ADVSPEC_X_SMEM_MAX: larger plain-bf16 inputs are read through L1 from global (measured faster)
+
 template <int B>
 cudaError_t launch_gemv_mma_t(const GemvParams& p, int device, cudaStream_t st, bool pdl) {
-  constexpr int kMaxDyn = 216 * 1024;  // + 8.5 KB static = 224.5 KB of the 227 KB a CTA may use
+  constexpr int kMaxDyn = 232448 - 9 * 1024;  // 227 KB per CTA minus the kernel's 8.5 KB of static shared memory
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = set_smem(gemv_mma_kernel<B>, kMaxDyn);
@@ -311,7 +314,7 @@ cudaError_t launch_gemv_mma_t(const GemvParams& p, int device, cudaStream_t st, 
   size_t x_smem = 0;
   if (p.in_mode == 1) {
     x_smem = xbytes;
-  } else if (xbytes + 4 * (size_t)kGmStageBytes <= (size_t)kMaxDyn) {
+  } else if (xbytes + 2 * (size_t)kGmStageBytes <= (size_t)kMaxDyn && xbytes <= g_x_smem_max) {
     x_in_smem = 1;
     x_smem = xbytes;
   }
@@ -340,7 +343,7 @@ cudaError_t launch_gemv_mma(const GemvParams& p, int b, int device, cudaStream_t
 cudaError_t launch_gemv(const GemvParams& p, int b, int device, cudaStream_t st, bool pdl) {
   if (g_gemv_impl == 3) {
     const bool ok3 = (p.K % 16 == 0) &&
-                     (p.in_mode != 1 || ((size_t)b * ((size_t)p.K * 2 + 16) + 2 * (size_t)kGmStageBytes + 256 <= (size_t)216 * 1024));
+                     (p.in_mode != 1 || ((size_t)b * ((size_t)p.K * 2 + 16) + 2 * (size_t)kGmStageBytes + 256 <= (size_t)(232448 - 9 * 1024)));
     if (ok3) return launch_gemv_mma(p, b, device, st, pdl);
     return launch_gemv_v1(p, b, device, st, pdl);
   }
@@ -407,9 +410,9 @@ cudaError_t launch_attn_decode(const AttnDecodeParams& p, int n_items, int DH, c
 
 int g_attn_impl = 2;  // 2: fused tensor-core decode attention (default); 1: scalar 3-kernel path (A/B, other head dims)
 
-cudaError_t launch_attn_decode2(const AttnDecode2Params& p, int n_items, int DH, cudaStream_t st, bool pdl) {
-  constexpr int NST = 3;
-  dim3 g(n_items), blk(128);
+cudaError_t launch_attn_decode2(const AttnDecode2Params& p, int n_ctas, int DH, cudaStream_t st, bool pdl) {
+  constexpr int NST = 6;
+  dim3 g(n_ctas), blk(256);
   if (DH == 128) {
     static bool done = false;
     const int smem = 16 * 128 * 2 + NST * 2 * 64 * 128 * 2;
@@ -476,9 +479,10 @@ struct advspec_engine {
   float *part_m = nullptr, *part_l = nullptr, *part_o = nullptr;
   AttnItem* items = nullptr;
   int items_cap = 0, n_items = 0, n_slots = 0;
-  AttnItem2* items2 = nullptr;  // fused tensor-core decode attention
-  int items2_cap = 0, n_items2 = 0;
-  int* tickets = nullptr;
+  // fused tensor-core decode attention: work decomposition of the current batch
+  int a2_opg = 1, a2_n_og = 1, a2_n_splits = 1, a2_ctas = 0;
+  int h_slots[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int* s_pos = nullptr;     // [max_seqs] absolute position of each batch entry's next token
   bool attn_fused = false;  // this engine's shape is served by attn_decode_mma_kernel
 
   // opponent state (device arrays indexed by slot)
@@ -486,6 +490,8 @@ struct advspec_engine {
   uint64_t* s_seeds = nullptr;
   int *s_suf_len = nullptr, *s_n_out = nullptr, *s_done = nullptr, *s_cur_tok = nullptr,
       *s_out = nullptr;
+  float* samp_best = nullptr;  // [max_seqs][kSampleChunks] partial winners of the sampler
+  int* samp_idx = nullptr;
 
   // host-side bookkeeping
   int prefix_gen = 0;     // id of the live prefix (0 = none)
@@ -638,9 +644,9 @@ void free_all(advspec_engine* e) {
   if (e->graph) cudaGraphExecDestroy(e->graph);
   void* ptrs[] = {e->w, e->inv_freq, e->rope_cos, e->rope_sin, e->pkv, e->skv, e->p_tokens, e->p_x,
                   e->p_xn, e->p_qkv, e->p_attn, e->p_h, e->prefill_logits, e->dx, e->dx_save, e->dq,
-                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->items, e->items2, e->tickets,
+                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->items, e->s_pos,
                   e->s_slots, e->s_forced, e->s_seeds, e->s_suf_len, e->s_n_out, e->s_done,
-                  e->s_cur_tok, e->s_out};
+                  e->s_cur_tok, e->s_out, e->samp_best, e->samp_idx};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -699,57 +705,26 @@ void build_items(advspec_engine* e, const std::vector<int>& slots, std::vector<A
   }
 }
 
-// Work items of the fused decode attention: per KV head, opponents are grouped so that a group's
-// query rows (opponents x G heads) fill one 16-row MMA tile; the prefix is cut into splits shared by
-// the whole group, each opponent's suffix is its own item; the group's last finisher combines.
-void build_items2(advspec_engine* e, const std::vector<int>& slots, std::vector<AttnItem2>* out, int* n_slots) {
+// Decomposition of the fused decode attention for a batch: per KV head, opponents are grouped so that
+// a group's query rows (opponents x G heads) fill one 16-row MMA tile; the prefix is cut into splits
+// shared by the whole group (one CTA per SM in total), each opponent's suffix is its own CTA.
+void plan_attn2(advspec_engine* e, const std::vector<int>& slots) {
   const auto& d = e->d;
   const int b = (int)slots.size();
   const int G = d.n_heads / d.n_kv_heads;
-  const int opg = std::max(1, 16 / G);  // opponents per group
+  const int opg = std::max(1, 16 / G);
   const int n_og = (b + opg - 1) / opg;
   const int groups = d.n_kv_heads * n_og;
-  // one wave: 2 CTAs per SM are resident; suffix items take b * Hkv of those slots
-  const int slots_left = std::max(groups, 2 * num_sms(e->device) - b * d.n_kv_heads);
+  const int slots_left = std::max(groups, num_sms(e->device) - b * d.n_kv_heads);
   int n_splits = std::max(1, slots_left / std::max(1, groups));
-  n_splits = std::min(n_splits, std::max(1, e->prefix_len / 256));
+  n_splits = std::min(n_splits, std::max(1, e->prefix_len / g_attn_min_split));
   n_splits = std::min(n_splits, 300);
-  *n_slots = n_splits + 1;
-  out->clear();
-  for (int hk = 0; hk < d.n_kv_heads; ++hk) {
-    for (int og = 0; og < n_og; ++og) {
-      AttnItem2 base{};
-      base.kv_head = hk;
-      base.group = hk * n_og + og;
-      const int o0 = og * opg, o1 = std::min(b, o0 + opg);
-      base.expected = n_splits + (o1 - o0);
-      base.grp_n_rows = 0;
-      for (int bi = o0; bi < o1; ++bi)
-        for (int g = 0; g < G; ++g) {
-          base.grp_b[base.grp_n_rows] = (unsigned char)bi;
-          base.grp_head[base.grp_n_rows] = (unsigned char)(hk * G + g);
-          base.grp_n_rows++;
-        }
-      for (int s = 0; s < n_splits; ++s) {
-        AttnItem2 it = base;
-        it.seq = -1;
-        it.tok_begin = (int)((int64_t)e->prefix_len * s / n_splits);
-        it.tok_end = (int)((int64_t)e->prefix_len * (s + 1) / n_splits);
-        it.slot = s;
-        it.row_off = 0;
-        it.n_rows = base.grp_n_rows;
-        out->push_back(it);
-      }
-      for (int bi = o0; bi < o1; ++bi) {
-        AttnItem2 it = base;
-        it.seq = slots[bi];
-        it.slot = n_splits;
-        it.row_off = (bi - o0) * G;
-        it.n_rows = G;
-        out->push_back(it);
-      }
-    }
-  }
+  e->a2_opg = opg;
+  e->a2_n_og = n_og;
+  e->a2_n_splits = n_splits;
+  e->a2_ctas = groups * (n_splits + opg);
+  e->n_slots = n_splits + 1;
+  for (int i = 0; i < 8; ++i) e->h_slots[i] = i < b ? slots[i] : 0;
 }
 
 // Enqueue one forward step (all layers + lm_head) for the batch in s_slots.
@@ -780,7 +755,6 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
     ADV_TRACE(e->stream, "gemv qkv");
     if (e->attn_fused) {
       AttnDecode2Params a2{};
-      a2.items = e->items2;
       a2.qkv = e->dqkv;
       a2.rope_cos = e->rope_cos;
       a2.rope_sin = e->rope_sin;
@@ -790,19 +764,22 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       a2.sk = suffix_k(e, l);
       a2.sv = suffix_v(e, l);
       a2.sstride = d.max_new_tokens;
-      a2.slots = e->s_slots;
-      a2.suf_len = e->s_suf_len;
+      a2.pos_b = e->s_pos;
+      for (int i = 0; i < 8; ++i) a2.slots[i] = e->h_slots[i];
       a2.prefix_len = e->prefix_len;
       a2.part_m = e->part_m;
       a2.part_l = e->part_l;
       a2.part_o = e->part_o;
-      a2.tickets = e->tickets;
-      a2.out = e->dattn;
+      a2.b = b;
       a2.H = d.n_heads;
       a2.Hkv = d.n_kv_heads;
+      a2.G = d.n_heads / d.n_kv_heads;
+      a2.opg = e->a2_opg;
+      a2.n_og = e->a2_n_og;
+      a2.n_splits = e->a2_n_splits;
       a2.n_slots = e->n_slots;
       a2.scale = 1.0f / sqrtf((float)d.head_dim);
-      E_CUDA(e, launch_attn_decode2(a2, e->n_items2, d.head_dim, e->stream, true));
+      E_CUDA(e, launch_attn_decode2(a2, e->a2_ctas, d.head_dim, e->stream, true));
       ADV_TRACE(e->stream, "attn_decode_mma");
       E_CUDA(e, launch_pdl(attn_decode_combine2_kernel, dim3(b * d.n_heads), dim3(128), 0, e->stream, true,
                            (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o, e->dattn,
@@ -888,12 +865,30 @@ SampleParams make_sample_params(advspec_engine* e, float temperature, int eos_id
   sp.eos_id = eos_id;
   sp.advance = advance ? 1 : 0;
   sp.forced = forced;
+  sp.pos_b = e->s_pos;
+  sp.prefix_len = e->prefix_len;
+  sp.part_best = forced ? nullptr : e->samp_best;
+  sp.part_idx = forced ? nullptr : e->samp_idx;
   sp.cur_tok = e->s_cur_tok;
   sp.embed = embed_w(e);
   sp.x = e->dx;
   sp.d = e->d.d_model;
   sp.embed_scale = e->d.embed_scale;
   return sp;
+}
+
+// Sampler = vocabulary scan on 64 CTAs per opponent + a one-CTA merge that also advances the
+// opponent and writes the next embedding.
+cudaError_t launch_sampler(advspec_engine* e, const SampleParams& sp, int n, bool pdl) {
+  if (sp.forced == nullptr) {
+    cudaError_t r = launch_pdl(sample_partial_kernel, dim3(kSampleChunks, n), dim3(256), 0, e->stream, pdl, sp,
+                               e->samp_best, e->samp_idx);
+    if (r != cudaSuccess) return r;
+    e->launches++;
+    pdl = true;
+  }
+  e->launches++;
+  return launch_pdl(sample_kernel, dim3(n), dim3(1024), 0, e->stream, pdl, sp);
 }
 
 advspec_status setup_batch(advspec_engine* e, const int32_t* seq_ids, int n, std::vector<int>* slots) {
@@ -929,17 +924,7 @@ advspec_status setup_batch(advspec_engine* e, const int32_t* seq_ids, int n, std
   e->n_items = (int)items.size();
   E_CUDA(e, cudaMemcpyAsync(e->items, items.data(), items.size() * sizeof(AttnItem), cudaMemcpyHostToDevice,
                             e->stream));
-  std::vector<AttnItem2> items2;
-  if (e->attn_fused) {
-    build_items2(e, *slots, &items2, &e->n_slots);
-    if ((int)items2.size() > e->items2_cap) {
-      e->fail("internal: %zu fused attention items exceed capacity %d", items2.size(), e->items2_cap);
-      return ADVSPEC_ERR_INVALID;
-    }
-    e->n_items2 = (int)items2.size();
-    E_CUDA(e, cudaMemcpyAsync(e->items2, items2.data(), items2.size() * sizeof(AttnItem2), cudaMemcpyHostToDevice,
-                              e->stream));
-  }
+  if (e->attn_fused) plan_attn2(e, *slots);
   E_CUDA(e, cudaStreamSynchronize(e->stream));  // items/slots vectors die with this scope
   return ADVSPEC_OK;
 }
@@ -1009,6 +994,8 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   g_trace = getenv("ADVSPEC_TRACE") != nullptr;
   if (const char* gi = getenv("ADVSPEC_GEMV_IMPL")) g_gemv_impl = std::max(1, std::min(3, atoi(gi)));
   if (const char* ai = getenv("ADVSPEC_ATTN_IMPL")) g_attn_impl = atoi(ai) == 1 ? 1 : 2;
+  if (const char* xm = getenv("ADVSPEC_X_SMEM_MAX")) g_x_smem_max = (size_t)atoll(xm);
+  if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
 
   auto boot = [&]() -> advspec_status {
     const auto& d = e->d;
@@ -1027,6 +1014,8 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, dmalloc(&e->pkv, (size_t)d.n_layers * 2 * e->pkv_layer_elems));
     E_CUDA(e, dmalloc(&e->skv, (size_t)d.n_layers * 2 * e->skv_layer_elems));
     e->C = std::min(4096, (d.max_prefix_tokens + 127) / 128 * 128);
+    if (const char* pc = getenv("ADVSPEC_PREFILL_CHUNK"))  // tests: force multi-chunk prefill on small prompts
+      e->C = std::max(128, std::min(e->C, atoi(pc) / 128 * 128));
     const size_t C = e->C, dm = d.d_model, QKV = qkv_dim(d), HD = (size_t)d.n_heads * d.head_dim;
     E_CUDA(e, dmalloc(&e->p_tokens, C));
     E_CUDA(e, dmalloc(&e->p_x, C * dm));
@@ -1053,10 +1042,8 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, dmalloc(&e->part_o, B * d.n_heads * (size_t)(max_splits + 1) * d.head_dim));
     e->items_cap = d.n_kv_heads * (((int)B * G + 3) / 4) * max_splits + (int)B * d.n_kv_heads * ((G + 3) / 4);
     E_CUDA(e, dmalloc(&e->items, (size_t)e->items_cap));
-    e->items2_cap = d.n_kv_heads * (int)B * (max_splits + 16);
-    E_CUDA(e, dmalloc(&e->items2, (size_t)e->items2_cap));
-    E_CUDA(e, dmalloc(&e->tickets, (size_t)d.n_kv_heads * B));
-    E_CUDA(e, cudaMemsetAsync(e->tickets, 0, (size_t)d.n_kv_heads * B * sizeof(int), e->stream));
+    E_CUDA(e, dmalloc(&e->s_pos, B));
+    E_CUDA(e, cudaMemsetAsync(e->s_pos, 0, B * sizeof(int), e->stream));
     e->attn_fused = g_attn_impl == 2 && (d.head_dim == 64 || d.head_dim == 128) && G <= 16 && d.n_heads <= 255;
     E_CUDA(e, dmalloc(&e->s_slots, B));
     E_CUDA(e, dmalloc(&e->s_forced, B));
@@ -1066,6 +1053,8 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, dmalloc(&e->s_done, B));
     E_CUDA(e, dmalloc(&e->s_cur_tok, B));
     E_CUDA(e, dmalloc(&e->s_out, B * (size_t)d.max_new_tokens));
+    E_CUDA(e, dmalloc(&e->samp_best, B * (size_t)kSampleChunks));
+    E_CUDA(e, dmalloc(&e->samp_idx, B * (size_t)kSampleChunks));
     E_CUDA(e, cudaMemsetAsync(e->s_suf_len, 0, B * sizeof(int), e->stream));
     E_CUDA(e, cudaMemsetAsync(e->s_n_out, 0, B * sizeof(int), e->stream));
     E_CUDA(e, cudaMemsetAsync(e->s_done, 0, B * sizeof(int), e->stream));
@@ -1344,8 +1333,7 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
   E_CUDA(e, cudaEventRecord(e->ev0, e->stream));
   // token 0 comes from the logits already on the device (the shared prefill's, or the last step's)
   SampleParams sp0 = make_sample_params(e, temperature, eos_id, e->logits_broadcast, false, nullptr, true);
-  E_CUDA(e, launch_pdl(sample_kernel, dim3(n), dim3(1024), 0, e->stream, false, sp0));
-  e->launches++;
+  E_CUDA(e, launch_sampler(e, sp0, n, false));
 
   const int steps = max_new - 1;
   const SampleParams sp = make_sample_params(e, temperature, eos_id, false, true, nullptr, true);
@@ -1356,7 +1344,7 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
     key.push_back(e->prefix_gen);
     { int tbits; memcpy(&tbits, &temperature, sizeof tbits); key.push_back(tbits); }
     key.push_back(eos_id);
-    const int64_t per_step = (e->attn_fused ? 6 : 7) * (int64_t)d.n_layers + 2;
+    const int64_t per_step = (e->attn_fused ? 6 : 7) * (int64_t)d.n_layers + 3;
     if (e->use_graph) {
       if (!e->graph || e->graph_key != key) {
         if (e->graph) {
@@ -1367,7 +1355,7 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
         E_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
         const int64_t before = e->launches;
         advspec_status fs = enqueue_forward(e, n, nullptr);
-        cudaError_t le = launch_pdl(sample_kernel, dim3(n), dim3(1024), 0, e->stream, true, sp);
+        cudaError_t le = launch_sampler(e, sp, n, true);
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
         e->launches = before;  // capture only records; launches are counted per replay
         if (fs != ADVSPEC_OK || le != cudaSuccess || ce != cudaSuccess) {
@@ -1393,8 +1381,7 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
       } else {
         advspec_status fs = enqueue_forward(e, n, nullptr);
         if (fs != ADVSPEC_OK) return fs;
-        E_CUDA(e, launch_pdl(sample_kernel, dim3(n), dim3(1024), 0, e->stream, true, sp));
-        e->launches++;
+        E_CUDA(e, launch_sampler(e, sp, n, true));
       }
       if (eos_id >= 0 && (s % 32) == 31) {
         int done_h[8];
@@ -1456,9 +1443,8 @@ advspec_status advspec_decode_step(advspec_engine* e, const int32_t* seq_ids, in
   }
   E_CUDA(e, cudaMemcpyAsync(e->s_forced, forced_tokens, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
   SampleParams sp = make_sample_params(e, 0.f, -1, false, false, e->s_forced, false);
-  E_CUDA(e, launch_pdl(sample_kernel, dim3(n), dim3(1024), 0, e->stream, false, sp));
+  E_CUDA(e, launch_sampler(e, sp, n, false));
   ADV_TRACE(e->stream, "sample(forced)");
-  e->launches++;
   st = enqueue_forward(e, n, nullptr);
   if (st != ADVSPEC_OK) return st;
   advance_kernel<<<1, n, 0, e->stream>>>(e->s_slots, e->s_suf_len);
@@ -1604,6 +1590,15 @@ advspec_status advspec_ktrace_read(advspec_engine* e, uint64_t* out, int32_t cap
   return ADVSPEC_OK;
 }
 
+advspec_status advspec_ktrace_phases(advspec_engine* e, uint64_t* out16) {
+  if (!e || !out16) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  E_CUDA(e, cudaSetDevice(e->device));
+  E_CUDA(e, cudaStreamSynchronize(e->stream));
+  E_CUDA(e, cudaMemcpyFromSymbol(out16, g_phase, 16 * sizeof(uint64_t)));
+  return ADVSPEC_OK;
+}
+
 // ------------------------------------------------------------- op-level
 static advspec_status op_begin(int device) {
   int ndev = 0;
@@ -1675,6 +1670,8 @@ advspec_status advspec_op_gemv(int32_t device, const void* W, const void* x, con
                reinterpret_cast<const float*>(bias), y, N, K, in_mode, epilogue, act, eps};
   if (const char* gi = getenv("ADVSPEC_GEMV_IMPL")) g_gemv_impl = std::max(1, std::min(3, atoi(gi)));
   if (const char* ai = getenv("ADVSPEC_ATTN_IMPL")) g_attn_impl = atoi(ai) == 1 ? 1 : 2;
+  if (const char* xm = getenv("ADVSPEC_X_SMEM_MAX")) g_x_smem_max = (size_t)atoll(xm);
+  if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
   cudaError_t r = launch_gemv(p, b, device, 0, false);
   if (r != cudaSuccess) {
     g_create_error = std::string("op_gemv launch: ") + cudaGetErrorString(r);

@@ -20,33 +20,35 @@
 
 namespace advspec {
 
-constexpr int kGmRT = 16;       // rows per tile (MMA M)
-constexpr int kGmKCDefault = 1024;  // columns per tile
+constexpr int kGmRTDefault = 16;    // rows per tile (8 = upper half of the MMA tile zero; measured slower)
+constexpr int kGmKCDefault = 2048;  // columns per tile: one 4 KB bulk copy per row
 constexpr int kGmMaxStages = 8;
-template <int KC>
+template <int KC, int RT = kGmRTDefault>
 struct GmCfg {
   static constexpr int kRowPitch = KC * 2 + 16;  // bytes; +16 staggers rows across banks
-  static constexpr int kStageBytes = kGmRT * kRowPitch;
+  static constexpr int kStageBytes = RT * kRowPitch;
   static constexpr int kWarpCols = KC / 8;       // columns of a tile owned by one consumer warp
   static constexpr int kSteps = kWarpCols / 16;  // MMA k-steps per warp per tile
 };
-constexpr int kGmStageBytes = GmCfg<kGmKCDefault>::kStageBytes;  // 33,024
+constexpr int kGmStageBytes = GmCfg<kGmKCDefault, kGmRTDefault>::kStageBytes;  // 65,792
 constexpr int kGmConsumers = 256;
 constexpr int kGmThreads = 288;
 
-template <int B, int KC = kGmKCDefault>
+template <int B, int KC = kGmKCDefault, int RT = kGmRTDefault>
 __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, int n_stages, int x_in_smem) {
+  static_assert(RT == 8 || RT == 16, "a tile is half or all of the 16-row MMA M dimension");
   constexpr int kGmKC = KC;
-  constexpr int kGmRowPitch = GmCfg<KC>::kRowPitch;
-  constexpr int kGmStageBytes = GmCfg<KC>::kStageBytes;
-  constexpr int kWC = GmCfg<KC>::kWarpCols;
-  constexpr int kSteps = GmCfg<KC>::kSteps;
+  constexpr int kGmRT = RT;
+  constexpr int kGmRowPitch = GmCfg<KC, RT>::kRowPitch;
+  constexpr int kGmStageBytes = GmCfg<KC, RT>::kStageBytes;
+  constexpr int kWC = GmCfg<KC, RT>::kWarpCols;
+  constexpr int kSteps = GmCfg<KC, RT>::kSteps;
   extern __shared__ __align__(128) uint8_t gm_smem[];
   uint8_t* ring = gm_smem;
   uint8_t* xs_raw = gm_smem + (size_t)n_stages * kGmStageBytes;  // bf16 [B][K] with pitch K*2+16
   const int xpitch = p.K * 2 + 16;
   __shared__ uint64_t full_bar[kGmMaxStages], empty_bar[kGmMaxStages];
-  __shared__ float s_part[2][8][kGmRT][8];
+  __shared__ float s_part[2][8][RT][8];
   __shared__ float s_red[8][B];
   __shared__ float s_inv[B];
 
@@ -67,7 +69,10 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
     fence_mbar_init();
   }
   __syncthreads();
-
+  // Let the next kernel's CTAs be scheduled as soon as SMs free up: everything they do before their
+  // own griddepcontrol.wait (priming their weight ring) is independent of this kernel's output.
+  if (!g_ktrace_on) pdl_launch_dependents();  // while tracing, kernels trigger at their end so that
+                                              // start-to-start stamps are clean per-kernel costs
   if (warp == 8) {
     // ------------------------------ producer ------------------------------
     for (int t = 0; t < n_tiles; ++t) {
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
         mbar_arrive_expect_tx(&full_bar[s], cbytes * (uint32_t)rows);
       }
       __syncwarp();
-      if (lane < rows)
+      if (lane < rows)  // rows <= RT
         bulk_load_1d(ring + (size_t)s * kGmStageBytes + (size_t)lane * kGmRowPitch,
                      p.W + (int64_t)(rb + lane) * p.K + kc, cbytes, &full_bar[s]);
     }
@@ -151,8 +156,9 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
     const bool opp_ok = n_opp < B;
     const uint8_t* xrow = xbase + (size_t)(opp_ok ? n_opp : 0) * xstride;
     // ldmatrix source row/column of this lane inside a 16 x 16 A block
-    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
-    const int a_col = (lane >> 4) * 8;
+    // ldmatrix source of this lane inside a 16 x 16 A block (RT == 8: a 8 x 16 block, x2 load)
+    const int a_row = (RT == 16) ? (lane & 7) + ((lane >> 3) & 1) * 8 : (lane & 7);
+    const int a_col = (RT == 16) ? (lane >> 4) * 8 : ((lane >> 3) & 1) * 8;
 
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int t = 0; t < n_tiles; ++t) {
@@ -177,7 +183,15 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
       for (int ks = 0; ks < kSteps; ++ks) {
         if (col0 + ks * 16 < p.K) {  // warp-uniform
           uint32_t a[4];
-          ldmatrix_x4(a, tile + ks * 32);
+          if constexpr (RT == 16) {
+            ldmatrix_x4(a, tile + ks * 32);
+          } else {
+            uint32_t lo, hi;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+                         : "=r"(lo), "=r"(hi)
+                         : "r"(smem_u32(tile + ks * 32)));
+            a[0] = lo; a[1] = 0u; a[2] = hi; a[3] = 0u;  // rows 8..15 of the MMA tile are zero
+          }
           mma_bf16_16816(acc, a, bf[ks][0], bf[ks][1]);
         }
       }
@@ -191,7 +205,8 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
         const int g = lane >> 2;
         // accumulator layout: acc[0],acc[1] = (row g, opponents 2*t4, 2*t4+1); acc[2],acc[3] = row g+8
         *reinterpret_cast<float2*>(&s_part[buf][warp][g][2 * t4]) = make_float2(acc[0], acc[1]);
-        *reinterpret_cast<float2*>(&s_part[buf][warp][g + 8][2 * t4]) = make_float2(acc[2], acc[3]);
+        if constexpr (RT == 16)
+          *reinterpret_cast<float2*>(&s_part[buf][warp][g + 8][2 * t4]) = make_float2(acc[2], acc[3]);
         acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
         named_bar_sync(1, kGmConsumers);
         if (p.epilogue == EPI_GATED_BF16) {

@@ -78,7 +78,7 @@ EXPORTED_SYMBOLS = [
     "advspec_decode", "advspec_decode_step", "advspec_get_logits", "advspec_prefill_logits",
     "advspec_release_seqs", "advspec_release_prefix", "advspec_prefix_kv_region",
     "advspec_prefix_adopt", "advspec_get_timing", "advspec_profile_decode_step",
-    "advspec_decode_step_bytes", "advspec_ktrace_enable", "advspec_ktrace_read", "advspec_op_gemm", "advspec_op_gemm_check", "advspec_op_gemv",
+    "advspec_decode_step_bytes", "advspec_ktrace_enable", "advspec_ktrace_read", "advspec_ktrace_phases", "advspec_op_gemm", "advspec_op_gemm_check", "advspec_op_gemv",
     "advspec_op_attn_prefill",
 ]
 
@@ -121,6 +121,7 @@ def load_library() -> C.CDLL:
         "advspec_decode_step_bytes": (i32, [vp, P(i32), i32, P(C.c_double), P(C.c_double)]),
         "advspec_ktrace_enable": (i32, [vp, i32]),
         "advspec_ktrace_read": (i32, [vp, P(C.c_uint64), i32, P(i32)]),
+        "advspec_ktrace_phases": (i32, [vp, P(C.c_uint64)]),
         "advspec_op_gemm": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32]),
         "advspec_op_gemm_check": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32]),
         "advspec_op_gemv": (i32, [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32]),
@@ -281,6 +282,11 @@ class Engine:
         n = C.c_int32()
         self._check(self.lib.advspec_ktrace_read(self.h, _p(buf, C.c_uint64), cap, C.byref(n)))
         return [(int(v) >> 4, int(v) & 15) for v in buf[: n.value]]
+
+    def ktrace_phases(self) -> list[int]:
+        buf = np.zeros(16, dtype=np.uint64)
+        self._check(self.lib.advspec_ktrace_phases(self.h, _p(buf, C.c_uint64)))
+        return [int(v) for v in buf]
 
     def decode_step_bytes(self, seq_ids: Sequence[int]) -> tuple[float, float]:
         ids = _i32(seq_ids)

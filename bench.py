@@ -302,13 +302,22 @@ def run_b200_arm(args, rank, world, local_rank):
     if rank == 0:
         peaks = measured_peaks()
         e = engine()
-        # roofline of the dominant kernel: one profiled decode step mid-generation
+        # roofline of the dominant kernel, measured IN SITU: the engine stamps the GPU's global timer
+        # at the start of every decode kernel inside the CUDA-graph replay; consecutive stamps give each
+        # kernel's real cost (run + launch gap).  Host-side events cannot time 5-40 us kernels without
+        # becoming CPU-bound, and ncu serialises them with cold caches.
+        from advspec_b200 import measure
+
         pid = e.prefill(_prompt_ids(spec, system_prompt, user_message))
         ids = e.fork(pid, [1 + i for i in range(args.opponents)])
         e.decode(ids, max(2, args.gen // 2), temperature=0.7)
         step_bytes, gemv_bytes = e.decode_step_bytes(ids)
-        prof = e.profile_decode_step(ids)
-        gemv_gbs = gemv_bytes / (prof.gemv_ms * 1e-3) / 1e9 if prof.gemv_ms > 0 else 0.0
+        e.ktrace_enable(True)
+        e.decode(ids, min(40, max(4, args.gen // 4)), temperature=0.7)
+        tl = measure.summarize(e.ktrace_read(), spec.n_layers)
+        e.ktrace_enable(False)
+        gemv_ms = tl.get("gemv_us_per_step", 0.0) / 1e3
+        gemv_gbs = gemv_bytes / (gemv_ms * 1e-3) / 1e9 if gemv_ms > 0 else 0.0
         e.release_prefix(pid)
         mean_prefill = sum(prefill_ms) / len(prefill_ms)
         mean_decode = sum(decode_ms) / len(decode_ms)
@@ -330,11 +339,14 @@ def run_b200_arm(args, rank, world, local_rank):
                     "wall_s": wall},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "gemv_kernel (weight-streaming GEMV, all decode matmuls)",
+            "roofline": {"bound": "hbm", "kernel": "gemv_mma_kernel (weight-streaming GEMV: every decode matmul)",
                          "achieved": gemv_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": gemv_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
-                         "algorithmic_bytes_per_step": gemv_bytes, "launches_per_step": prof.gemv_launches,
-                         "kernel_ms_per_step": prof.gemv_ms, "traffic": None},
+                         "algorithmic_bytes_per_step": gemv_bytes,
+                         "launches_per_step": tl.get("gemv_launches_per_step"),
+                         "kernel_ms_per_step": gemv_ms, "traffic": None,
+                         "how": "device global-timer stamps at kernel entry inside the graph replay; cost = run + launch gap",
+                         "timeline": {k: round(v["us_each"], 2) for k, v in tl.get("rows", {}).items()}},
             "decode": {"ms_per_step": step_ms, "batch": args.opponents, "algorithmic_bytes_per_step": step_bytes,
                        "achieved_gbs": decode_gbs, "frac_of_hbm_peak": decode_gbs / peaks["hbm_gbs"],
                        "tokens_per_s_per_gpu": args.opponents / (step_ms * 1e-3)},

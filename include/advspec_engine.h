@@ -198,6 +198,9 @@ advspec_status advspec_decode_step_bytes(advspec_engine *e,
 advspec_status advspec_ktrace_enable(advspec_engine *e, int32_t on);
 advspec_status advspec_ktrace_read(advspec_engine *e, uint64_t *out, int32_t cap,
                                    int32_t *n);
+/* Diagnostic: 16 phase stamps (ns) left by one CTA of the last instrumented kernel
+ * launch while tracing was on (where inside the kernel the time goes). */
+advspec_status advspec_ktrace_phases(advspec_engine *e, uint64_t *out16);
 
 /* ---- op-level entry points (device pointers; used by tests/) ------------- */
 

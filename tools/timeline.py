@@ -19,40 +19,16 @@ tm0 = e.timing()
 e.ktrace_enable(True)
 e.decode(ids, 40, temperature=0.7)
 tr = e.ktrace_read()
+ph = e.ktrace_phases()
 e.ktrace_enable(False)
 tm = e.timing()
 step_bytes, gemv_bytes = e.decode_step_bytes(ids)
-ts = np.array([t for t, k in tr], dtype=np.int64); kinds = np.array([k for t, k in tr])
-# steps are delimited by the sampler (kind 3)
-samp = np.where(kinds == 3)[0]
-per_step = []
-for a, z in zip(samp[1:-1], samp[2:]):
-    d = np.diff(ts[a:z + 1])            # cost of kernel i = start(i+1) - start(i)
-    per_step.append((kinds[a:z], d))
-L = spec.n_layers
-kpl = (len(per_step[0][0]) - 2) // L    # kernels per layer
-names = {1: "gemv", 2: "attn", 3: "sample", 4: "rope", 5: "combine"}
-agg = {}
-for ks, d in per_step:
-    # layout: sample, then L x [kpl kernels], then lm_head gemv
-    for i, (k, dt) in enumerate(zip(ks, d)):
-        if i == 0: key = "sample+embed"
-        elif i == len(ks) - 1: key = "gemv lm_head"
-        else:
-            pos = (i - 1) % kpl
-            key = f"L[{pos}] {names[int(k)]}"
-        agg.setdefault(key, []).append(float(dt))
-tot = sum(np.sum(v) for v in agg.values()) / len(per_step)
+from advspec_b200 import measure
+tl = measure.summarize(tr, spec.n_layers)
 out = {"model": name, "b": b, "prompt": ptok, "decode_ms_per_step_events": tm.decode_ms / max(tm.decode_steps, 1),
-       "timeline_us_per_step": tot / 1e3, "kernels_per_step": len(per_step[0][0]), "steps_seen": len(per_step),
-       "gemv_impl": os.environ.get("ADVSPEC_GEMV_IMPL", "3"), "rows": {}}
-gemv_ns = 0.0
-for k, v in agg.items():
-    per = np.sum(v) / len(per_step)
-    n = len(v) / len(per_step)
-    out["rows"][k] = {"n_per_step": n, "us_each": per / n / 1e3, "us_per_step": per / 1e3, "share": per / tot}
-    if "gemv" in k: gemv_ns += per
-out["gemv_us_per_step"] = gemv_ns / 1e3
-out["gemv_gbs"] = gemv_bytes / gemv_ns
-out["step_gbs"] = step_bytes / tot
+       "timeline_us_per_step": tl["us_per_step"], "kernels_per_step": tl["kernels_per_step"], "steps_seen": tl["steps"],
+       "gemv_impl": os.environ.get("ADVSPEC_GEMV_IMPL", "3"), "rows": tl["rows"],
+       "gemv_us_per_step": tl["gemv_us_per_step"], "gemv_gbs": gemv_bytes / (tl["gemv_us_per_step"] * 1e3),
+       "step_gbs": step_bytes / (tl["us_per_step"] * 1e3)}
+out["attn_phases_ns"] = [ph[i + 1] - ph[i] for i in range(5)]
 print(json.dumps(out, indent=1))
