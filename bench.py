@@ -38,6 +38,7 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
+_emit = lambda line: print(json.dumps(line), flush=True)
 METRIC = "aggregate_critique_tokens_per_sec"
 UNIT = "tokens/s"
 
@@ -53,8 +54,8 @@ def parse_args():
     ap.add_argument("--spec-tokens", type=int, default=4096)
     ap.add_argument("--gen", type=int, default=256, help="new tokens per opponent (the CLI's 8000 cap, bounded)")
     ap.add_argument("--doc-type", default="prd")
-    ap.add_argument("--cpu-sample-layers", type=int, default=2)
-    ap.add_argument("--cpu-sample-gen", type=int, default=8)
+    ap.add_argument("--cpu-sample-layers", type=int, default=1)
+    ap.add_argument("--cpu-sample-gen", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -223,7 +224,7 @@ def run_reference_arm(args, rank, world):
         "note": "reference fan-out (models.py:681-722) restated over a CPU HF model; litellm and the "
                 "reference tree do not exist on this box; whole-workload time is estimated from a bounded sample",
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -365,7 +366,7 @@ def run_b200_arm(args, rank, world, local_rank):
             except Exception as ex:  # the baseline must never sink the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "port",
                                         "sample": f"failed: {ex}"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -379,6 +380,12 @@ def _prompt_ids(spec, system_prompt, user_message):
 
 
 def main():
+    # Libraries (NCCL's version banner, HF warnings) must not share stdout with the ONE JSON line the
+    # driver parses: everything written to fd 1 goes to stderr, the JSON goes to the saved real stdout.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda line: (real_stdout.write(json.dumps(line) + "\n"), real_stdout.flush())
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
