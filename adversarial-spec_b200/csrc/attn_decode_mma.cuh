@@ -28,6 +28,8 @@ struct AttnDecode2Params {
   __nv_bfloat16* sk;         // suffix K [max_seqs][Hkv][sstride][DH] (this layer)
   __nv_bfloat16* sv;
   int64_t sstride;
+  const CUtensorMap* maps;   // [0] prefix K, [1] prefix V of this layer: 2-D (Hkv*pstride tokens) x DH,
+                             // box 64 tokens x 64 dims, 128-byte swizzle
   const int* pos_b;          // [b] absolute position of each opponent's new token (device state)
   int slots[8];              // batch index -> opponent slot (fixed for the decode call)
   int prefix_len;
@@ -44,9 +46,15 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   constexpr int BN = 64;
   constexpr int CPR = DH / 8;
   constexpr int TILE = BN * DH;  // elements of one K (or V) tile
-  extern __shared__ __align__(128) uint8_t ad_smem[];
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(ad_smem);  // [16][DH]
-  __nv_bfloat16* sKV = sQ + 16 * DH;                               // [NST][2][BN][DH]
+  constexpr int NH = DH / 64;    // 128-byte-wide halves of a row (TMA swizzle atoms are 128 B wide)
+  constexpr int HALF = BN * 64;  // elements of one 64-token x 64-dim half tile (8 KB)
+  extern __shared__ uint8_t ad_smem_raw[];
+  // ring first, 1024-byte aligned (128-byte TMA swizzle atoms); then the query tile; then barriers
+  uint8_t* ad_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ad_smem_raw) + 1023) &
+                                                ~static_cast<uintptr_t>(1023));
+  __nv_bfloat16* sKV = reinterpret_cast<__nv_bfloat16*>(ad_smem);  // [NST][K halves | V halves][64][64]
+  __nv_bfloat16* sQ = sKV + (size_t)NST * 2 * TILE;                // [16][DH]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sQ + 16 * DH);  // [NST]
 
   ktrace_mark(TK_ATTN);
   phase_mark(0);
@@ -56,7 +64,10 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   const int g = lane >> 2, t4 = lane & 3;
   const int QKV = (p.H + 2 * p.Hkv) * DH;
   constexpr int half = DH / 2;
-  auto swz = [](int row, int chunk) { return row * DH + ((chunk ^ (row & 7)) << 3); };
+  auto swz = [](int row, int chunk) { return row * DH + ((chunk ^ (row & 7)) << 3); };  // query tile
+  // K/V tiles: element offset of 16-byte chunk `chunk` (8 dims) of token row `row` in the layout TMA
+  // writes with CU_TENSOR_MAP_SWIZZLE_128B: half tiles of [64 tokens][64 dims], chunk index XOR (row % 8)
+  auto kvz = [](int row, int chunk) { return (chunk >> 3) * HALF + row * 64 + (((chunk & 7) ^ (row & 7)) << 3); };
 
   // ---- which item am I
   const int per_group = p.n_splits + p.opg;
@@ -69,6 +80,12 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   const int row_off = is_prefix ? 0 : (j - p.n_splits) * p.G;  // rows inside the group's 16-row tile
   const int n_rows = is_prefix ? n_opp * p.G : p.G;
   const int slot_out = is_prefix ? j : p.n_splits;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) mbar_init(&full_bar[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
 
   const __nv_bfloat16 *kb, *vb;
   int tb, te;
@@ -103,17 +120,32 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   }
 
   const int n_tiles = (te - tb + BN - 1) / BN;
+  // Prefix tiles: one elected thread issues 2*NH TMA box copies per tile (K and V halves) that complete
+  // on the stage's mbarrier.  Suffix tiles (a handful of tokens the CTA itself just extended): per-lane
+  // cp.async into the same swizzled layout.
   auto load_tile = [&](int tile) {
     const int st = tile % NST;
     const int k0 = tb + tile * BN;
     __nv_bfloat16* dK = sKV + (size_t)st * 2 * TILE;
     __nv_bfloat16* dV = dK + TILE;
-    for (int id = tid; id < BN * CPR; id += 256) {
-      const int r = id / CPR, c = id % CPR;
-      const bool ok = (k0 + r) < te;
-      const int64_t off = (int64_t)(ok ? k0 + r : tb) * DH + c * 8;
-      cp_async16(dK + swz(r, c), kb + off, ok);
-      cp_async16(dV + swz(r, c), vb + off, ok);
+    if (is_prefix) {
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&full_bar[st], 2u * TILE * 2u);
+        const int row0 = hk * (int)p.pstride + k0;
+#pragma unroll
+        for (int h2 = 0; h2 < NH; ++h2) {
+          tma_load_2d(dK + h2 * HALF, &p.maps[0], &full_bar[st], h2 * 64, row0);
+          tma_load_2d(dV + h2 * HALF, &p.maps[1], &full_bar[st], h2 * 64, row0);
+        }
+      }
+    } else {
+      for (int id = tid; id < BN * CPR; id += 256) {
+        const int r = id / CPR, c = id % CPR;
+        const bool ok = (k0 + r) < te;
+        const int64_t off = (int64_t)(ok ? k0 + r : tb) * DH + c * 8;
+        cp_async16(dK + kvz(r, c), kb + off, ok);
+        cp_async16(dV + kvz(r, c), vb + off, ok);
+      }
     }
   };
   // Put the whole slice in flight at once when it fits the ring (prefix KV is constant during decode,
@@ -182,9 +214,13 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   const float sl2 = p.scale * 1.4426950408889634f;
 
   for (int jt = 0; jt < n_tiles; ++jt) {
-    // tiles 0..NST-1 were issued up front; tile jt >= NST was issued at iteration jt - NST + 1
-    cp_async_wait<NST - 1>();
-    __syncthreads();
+    // tiles 0..NST-1 were issued up front; tile jt >= NST was issued at iteration jt - NST
+    if (is_prefix) {
+      mbar_wait(&full_bar[jt % NST], (uint32_t)(jt / NST) & 1u, 0x700u + (jt % NST));
+    } else {
+      cp_async_wait<NST - 1>();
+      __syncthreads();
+    }
     if ((jt & 1) == wg) {
       const __nv_bfloat16* bK = sKV + (size_t)(jt % NST) * 2 * TILE;
       const __nv_bfloat16* bV = bK + TILE;
@@ -197,7 +233,7 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
         for (int kk = 0; kk < DH / 16; ++kk) {
           uint32_t r[4];
           const int mi = lane >> 3;
-          ldmatrix_x4(r, bK + swz(w4 * 16 + (mi >> 1) * 8 + (lane & 7), kk * 2 + (mi & 1)));
+          ldmatrix_x4(r, bK + kvz(w4 * 16 + (mi >> 1) * 8 + (lane & 7), kk * 2 + (mi & 1)));
           mma_bf16_16816(s[0], qf[kk], r[0], r[1]);
           mma_bf16_16816(s[1], qf[kk], r[2], r[3]);
         }
@@ -245,7 +281,7 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
         for (int db2 = 0; db2 < DH / 16; ++db2) {
           uint32_t r[4];
           const int mi = lane >> 3;
-          ldmatrix_x4_trans(r, bV + swz(w4 * 16 + (mi & 1) * 8 + (lane & 7), db2 * 2 + (mi >> 1)));
+          ldmatrix_x4_trans(r, bV + kvz(w4 * 16 + (mi & 1) * 8 + (lane & 7), db2 * 2 + (mi >> 1)));
           mma_bf16_16816(o[2 * db2], a, r[0], r[1]);
           mma_bf16_16816(o[2 * db2 + 1], a, r[2], r[3]);
         }

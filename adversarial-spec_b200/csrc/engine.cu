@@ -180,7 +180,17 @@ cudaError_t launch_gemm(const void* A, int64_t lda, int64_t a_rows, const void* 
     if (err) *err = "gemm: operands must be 16-byte aligned with pitches that are multiples of 8";
     return cudaErrorInvalidValue;
   }
-  const bool wide = p.N > 128;
+  // Tile width: the persistent grid runs ceil(tiles / SMs) waves of tiles whose time is ~ BN, so
+  // pick the BN in {128, 256} with the smaller waves x BN product (wave quantisation costs up to 14 %
+  // on the N = 4096 / 6144 matrices with BN = 256).
+  bool wide = p.N > 128;
+  if (wide) {
+    const int sms = num_sms(device);
+    const int64_t mt = (p.M + kGemmBM - 1) / kGemmBM;
+    const int64_t t256 = mt * ((p.N + 255) / 256), t128 = mt * ((p.N + 127) / 128);
+    const int64_t c256 = (t256 + sms - 1) / sms * 256, c128 = (t128 + sms - 1) / sms * 128;
+    wide = c256 <= c128 + c128 / 32;  // prefer the wide tile unless the narrow one wins by > 3 %
+  }
   CUtensorMap ta, tb;
   if (!make_tmap(&ta, A, a_rows, p.K, lda, kGemmBM) ||
       !make_tmap(&tb, B, p.N, p.K, ldb, wide ? 256 : 128)) {
@@ -415,7 +425,7 @@ cudaError_t launch_attn_decode2(const AttnDecode2Params& p, int n_ctas, int DH, 
   dim3 g(n_ctas), blk(256);
   if (DH == 128) {
     static bool done = false;
-    const int smem = 16 * 128 * 2 + NST * 2 * 64 * 128 * 2;
+    const int smem = 16 * 128 * 2 + NST * 2 * 64 * 128 * 2 + 1024 + 128;  // + alignment slack + barriers
     if (!done) {
       cudaError_t e = set_smem(attn_decode_mma_kernel<128, NST>, smem);
       if (e != cudaSuccess) return e;
@@ -425,7 +435,7 @@ cudaError_t launch_attn_decode2(const AttnDecode2Params& p, int n_ctas, int DH, 
   }
   if (DH == 64) {
     static bool done = false;
-    const int smem = 16 * 64 * 2 + NST * 2 * 64 * 64 * 2;
+    const int smem = 16 * 64 * 2 + NST * 2 * 64 * 64 * 2 + 1024 + 128;
     if (!done) {
       cudaError_t e = set_smem(attn_decode_mma_kernel<64, NST>, smem);
       if (e != cudaSuccess) return e;
@@ -483,6 +493,7 @@ struct advspec_engine {
   int a2_opg = 1, a2_n_og = 1, a2_n_splits = 1, a2_ctas = 0;
   int h_slots[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int* s_pos = nullptr;     // [max_seqs] absolute position of each batch entry's next token
+  CUtensorMap* kv_maps = nullptr;  // [L][2] device copies: prefix K / V tensor maps of each layer
   bool attn_fused = false;  // this engine's shape is served by attn_decode_mma_kernel
 
   // opponent state (device arrays indexed by slot)
@@ -644,7 +655,7 @@ void free_all(advspec_engine* e) {
   if (e->graph) cudaGraphExecDestroy(e->graph);
   void* ptrs[] = {e->w, e->inv_freq, e->rope_cos, e->rope_sin, e->pkv, e->skv, e->p_tokens, e->p_x,
                   e->p_xn, e->p_qkv, e->p_attn, e->p_h, e->prefill_logits, e->dx, e->dx_save, e->dq,
-                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->items, e->s_pos,
+                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->items, e->s_pos, e->kv_maps,
                   e->s_slots, e->s_forced, e->s_seeds, e->s_suf_len, e->s_n_out, e->s_done,
                   e->s_cur_tok, e->s_out, e->samp_best, e->samp_idx};
   for (void* p : ptrs)
@@ -764,6 +775,7 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       a2.sk = suffix_k(e, l);
       a2.sv = suffix_v(e, l);
       a2.sstride = d.max_new_tokens;
+      a2.maps = e->kv_maps + 2 * l;
       a2.pos_b = e->s_pos;
       for (int i = 0; i < 8; ++i) a2.slots[i] = e->h_slots[i];
       a2.prefix_len = e->prefix_len;
@@ -1045,6 +1057,21 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, dmalloc(&e->s_pos, B));
     E_CUDA(e, cudaMemsetAsync(e->s_pos, 0, B * sizeof(int), e->stream));
     e->attn_fused = g_attn_impl == 2 && (d.head_dim == 64 || d.head_dim == 128) && G <= 16 && d.n_heads <= 255;
+    if (e->attn_fused) {
+      std::vector<CUtensorMap> hm((size_t)d.n_layers * 2);
+      for (int l = 0; l < d.n_layers; ++l) {
+        const int64_t rows = (int64_t)d.n_kv_heads * d.max_prefix_tokens;
+        if (!make_tmap(&hm[2 * l], prefix_k(e, l), rows, d.head_dim, d.head_dim, 64) ||
+            !make_tmap(&hm[2 * l + 1], prefix_v(e, l), rows, d.head_dim, d.head_dim, 64)) {
+          e->fail("cuTensorMapEncodeTiled failed for the prefix KV of layer %d", l);
+          return ADVSPEC_ERR_CUDA;
+        }
+      }
+      E_CUDA(e, dmalloc(&e->kv_maps, hm.size()));
+      E_CUDA(e, cudaMemcpyAsync(e->kv_maps, hm.data(), hm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice,
+                                e->stream));
+      E_CUDA(e, cudaStreamSynchronize(e->stream));
+    }
     E_CUDA(e, dmalloc(&e->s_slots, B));
     E_CUDA(e, dmalloc(&e->s_forced, B));
     E_CUDA(e, dmalloc(&e->s_seeds, B));

@@ -50,8 +50,6 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
   __shared__ uint64_t full_bar[kGmMaxStages], empty_bar[kGmMaxStages];
   __shared__ float s_part[2][8][RT][8];
   __shared__ float s_red[8][B];
-  __shared__ float s_inv[B];
-
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   ktrace_mark(TK_GEMV);
   const int pairs = (p.N + 1) / 2;
@@ -99,15 +97,34 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
     const uint8_t* xbase;  // bf16 rows of x, pitch xstride bytes
     int xstride;
     if (p.in_mode == 1) {
+      // Fused RMSNorm of the fp32 residual stream.  When b*K is small (every model's d_model at b <= 4)
+      // the row slice of each thread stays in registers between the sum of squares and the scaling.
       const float* xf = reinterpret_cast<const float*>(p.x);
+      constexpr int kMaxV = 4;  // float4 per opponent per thread held in registers: K <= 4096
+      const bool in_regs = p.K <= kMaxV * kGmConsumers * 4;
+      float4 xv[B][kMaxV];
       float ss[B];
 #pragma unroll
       for (int b = 0; b < B; ++b) ss[b] = 0.f;
-      for (int k = tid * 4; k < p.K; k += kGmConsumers * 4) {
+      if (in_regs) {
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-          const float4 v = *reinterpret_cast<const float4*>(xf + (int64_t)b * p.K + k);
-          ss[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        for (int i = 0; i < kMaxV; ++i) {
+          const int k = (tid + i * kGmConsumers) * 4;
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            xv[b][i] = (k < p.K) ? *reinterpret_cast<const float4*>(xf + (int64_t)b * p.K + k)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            ss[b] += xv[b][i].x * xv[b][i].x + xv[b][i].y * xv[b][i].y + xv[b][i].z * xv[b][i].z +
+                     xv[b][i].w * xv[b][i].w;
+          }
+        }
+      } else {
+        for (int k = tid * 4; k < p.K; k += kGmConsumers * 4) {
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            const float4 v = *reinterpret_cast<const float4*>(xf + (int64_t)b * p.K + k);
+            ss[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          }
         }
       }
 #pragma unroll
@@ -116,22 +133,40 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
         if (lane == 0) s_red[warp][b] = t;
       }
       named_bar_sync(1, kGmConsumers);
-      if (tid < B) {
-        float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += s_red[w][tid];
-        s_inv[tid] = rsqrtf(t / (float)p.K + p.eps);
-      }
-      named_bar_sync(1, kGmConsumers);
-      for (int k = tid * 4; k < p.K; k += kGmConsumers * 4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(p.norm_w + k);
+      float inv[B];
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-          const float4 v = *reinterpret_cast<const float4*>(xf + (int64_t)b * p.K + k);
-          const float inv = s_inv[b];
-          uint2 o;
-          o.x = pack_bf16(v.x * inv * w4.x, v.y * inv * w4.y);
-          o.y = pack_bf16(v.z * inv * w4.z, v.w * inv * w4.w);
-          *reinterpret_cast<uint2*>(xs_raw + (size_t)b * xpitch + (size_t)k * 2) = o;
+      for (int b = 0; b < B; ++b) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_red[w][b];  // same fixed order in every thread
+        inv[b] = rsqrtf(t / (float)p.K + p.eps);
+      }
+      if (in_regs) {
+#pragma unroll
+        for (int i = 0; i < kMaxV; ++i) {
+          const int k = (tid + i * kGmConsumers) * 4;
+          if (k < p.K) {
+            const float4 w4 = *reinterpret_cast<const float4*>(p.norm_w + k);
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+              uint2 o;
+              o.x = pack_bf16(xv[b][i].x * inv[b] * w4.x, xv[b][i].y * inv[b] * w4.y);
+              o.y = pack_bf16(xv[b][i].z * inv[b] * w4.z, xv[b][i].w * inv[b] * w4.w);
+              *reinterpret_cast<uint2*>(xs_raw + (size_t)b * xpitch + (size_t)k * 2) = o;
+            }
+          }
+        }
+      } else {
+        for (int k = tid * 4; k < p.K; k += kGmConsumers * 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(p.norm_w + k);
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            const float4 v = *reinterpret_cast<const float4*>(xf + (int64_t)b * p.K + k);
+            uint2 o;
+            o.x = pack_bf16(v.x * inv[b] * w4.x, v.y * inv[b] * w4.y);
+            o.y = pack_bf16(v.z * inv[b] * w4.z, v.w * inv[b] * w4.w);
+            *reinterpret_cast<uint2*>(xs_raw + (size_t)b * xpitch + (size_t)k * 2) = o;
+          }
         }
       }
       named_bar_sync(1, kGmConsumers);

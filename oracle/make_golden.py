@@ -138,7 +138,7 @@ def make_hf_logits() -> None:
 
     import transformers
 
-    for name in ["tiny-llama", "tiny-llama-128", "tiny-qwen2", "tiny-gemma"]:
+    for name in ["tiny-llama", "tiny-llama-128", "tiny-qwen2", "tiny-gemma", "tiny-phi3", "tiny-gemma256"]:
         spec = model_spec.resolve(name)
         model = hf_oracle.build_hf_model(spec, 1234)
         toks = np.random.default_rng(7).integers(0, spec.vocab_size, 24)

@@ -8,7 +8,7 @@ from tests.gpu_util import TOL_MAX, TOL_RMS, make_engine, rel_errors
 
 pytestmark = pytest.mark.gpu
 
-MODELS = ["tiny-llama", "tiny-llama-128", "tiny-qwen2", "tiny-gemma"]
+MODELS = ["tiny-llama", "tiny-llama-128", "tiny-qwen2", "tiny-gemma", "tiny-phi3", "tiny-gemma256"]
 
 
 def _tokens(spec, n, seed):
@@ -229,8 +229,13 @@ def test_full_size_properties_llama3_8b(cuda_device, diag):
     for t in cont:
         e.decode_step(ids, [t, t, t])
     trio = e.get_logits(3)
-    diag["full_size/batch_invariance_maxabs"] = float(np.abs(trio - solo[None]).max())
-    assert np.abs(trio - solo[None]).max() < 1e-2 * float(solo.std())
+    mxb, rmsb = rel_errors(trio[0], solo)
+    diag["full_size/batch_invariance"] = {"max": mxb, "rms": rmsb}
+    # b = 1 and b = 3 cut the prefix into different numbers of slices, so bf16 P-roundings differ
+    # slightly per layer; same sqrt(layers) drift as above, nowhere near the O(1) of a wrong kernel
+    assert mxb < 0.3 and rmsb < 0.08, (mxb, rmsb)
+    assert float(np.abs(trio[0] - trio[1]).max()) == 0.0 and float(np.abs(trio[0] - trio[2]).max()) == 0.0, \
+        "identical opponents in one batch must produce identical logits"
     res = e.decode(ids, 6, temperature=0.0)
     assert res.tokens[0] == res.tokens[1] == res.tokens[2] and res.lens == [6, 6, 6]
     tm = e.timing()
