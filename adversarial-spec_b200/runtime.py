@@ -221,3 +221,48 @@ def reduce_round_stats(max_values: Sequence[float], sum_values: Sequence[int], d
 def shard_panels(n_panels: int, rank: int, world: int) -> list[int]:
     """Independent panels (or opponents of a heterogeneous panel) -> ranks, round-robin."""
     return [i for i in range(n_panels) if i % world == rank]
+
+
+# ----------------------------------------------------------------------------- replica placement
+class _DevMem:
+    """Lets torch alias a raw device allocation of the engine (no copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def device_bytes_tensor(ptr: int, nbytes: int, device: int):
+    import torch
+
+    return torch.as_tensor(_DevMem(ptr, nbytes), device=f"cuda:{device}")
+
+
+def replicate_prefix(engine, prompt_ids: Sequence[int], rank: int, src: int = 0, broadcast=None,
+                     alias=None, device: int = 0) -> int:
+    """Same-weight replicas one per GPU: rank `src` prefills the shared prompt ONCE,
+    then its prefix KV region and last-position logits are broadcast (NCCL over NVLink) and the other
+    ranks adopt them instead of recomputing the prefill.  This is the path's only real exchange step.
+    Returns the local prefix id.  `broadcast`/`alias` are injectable for the gloo CPU test."""
+    import torch
+    import torch.distributed as dist
+
+    broadcast = broadcast or (lambda t: dist.broadcast(t, src=src))
+    alias = alias or (lambda ptr, n: device_bytes_tensor(ptr, n, device))
+    vocab = engine.spec.vocab_size
+    if rank == src:
+        pid = engine.prefill(prompt_ids)
+        logits = torch.from_numpy(engine.get_logits(1)[0].copy())
+    else:
+        pid = None
+        logits = torch.empty(vocab, dtype=torch.float32)
+    on_gpu = torch.cuda.is_available() and alias is not None and dist.is_initialized() and dist.get_backend() == "nccl"
+    lg = logits.cuda(device) if on_gpu else logits
+    broadcast(lg)
+    if rank != src:
+        pid = engine.prefix_adopt(len(prompt_ids), lg.cpu().numpy())
+    ptr, nbytes = engine.prefix_kv_region(pid)
+    kv = alias(ptr, nbytes)
+    broadcast(kv)
+    if on_gpu:
+        torch.cuda.synchronize(device)
+    return pid

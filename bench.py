@@ -299,6 +299,34 @@ def run_b200_arm(args, rank, world, local_rank):
                                                                         device="cuda")
     out_tokens, launches = int(out_tokens), int(launches)
 
+    # Extra, N > 1 only: the SAME 'world'-opponent panel spread one opponent per GPU (configs[1]'s literal
+    # placement) with the prefix prefilled once on rank 0 and its KV broadcast over NVLink, against every
+    # rank recomputing the prefill.  Reported beside the headline; SURVEY.md §8(e) asks for all three.
+    spread = None
+    if world > 1:
+        prompt_ids = _prompt_ids(spec, system_prompt, user_message)
+        e = engine()
+
+        def spread_round(broadcast: bool):
+            barrier()
+            t0 = time.perf_counter()
+            if broadcast:
+                pid = runtime.replicate_prefix(e, prompt_ids, rank, src=0, device=local_rank)
+            else:
+                pid = e.prefill(prompt_ids)
+            ids = e.fork(pid, [runtime.opponent_seed(7, rank)])
+            res = e.decode(ids, args.gen, temperature=0.7)
+            e.release_prefix(pid)
+            barrier()
+            return time.perf_counter() - t0, sum(res.lens)
+
+        spread = {}
+        for mode, bc in (("kv_broadcast", True), ("recompute", False)):
+            spread_round(bc)  # warm (NCCL communicator, graph for b = 1)
+            times, toks = zip(*[spread_round(bc) for _ in range(max(1, args.steps))])
+            (tmax,), (tsum,) = runtime.reduce_round_stats([sum(times)], [sum(toks)], device="cuda")
+            spread[mode] = {"tokens_per_s": tsum / tmax, "s_per_round": tmax / len(times), "opponents": world}
+
     line = None
     if rank == 0:
         peaks = measured_peaks()
@@ -355,6 +383,9 @@ def run_b200_arm(args, rank, world, local_rank):
                         "tflops": prefill_tflops, "frac_of_bf16_peak": prefill_tflops / peaks["bf16_tflops"],
                         "shared_by_opponents": args.opponents},
         }
+        if spread is not None:
+            line["replica_spread"] = dict(spread, note="one opponent per GPU, one panel of n_gpus opponents; wall "
+                                          "time incl. host calls; headline `value` is the co-batched weak-scaling run")
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)

@@ -49,3 +49,71 @@ def test_single_process_is_identity():
 
     assert runtime.reduce_round_stats([1.5], [3]) == ([1.5], [3])
     assert runtime.shard_panels(3, 0, 1) == [0, 1, 2]
+
+
+class _FakeEngine:
+    """Host-memory stand-in with the engine's replica-placement surface (the real one needs a GPU)."""
+
+    def __init__(self, vocab, kv_bytes):
+        import numpy as np
+        from types import SimpleNamespace
+
+        self.spec = SimpleNamespace(vocab_size=vocab)
+        self.kv = np.zeros(kv_bytes, dtype=np.uint8)
+        self.logits = None
+        self.adopted = None
+
+    def prefill(self, ids):
+        import numpy as np
+
+        self.kv[:] = (np.arange(self.kv.size) * 7 + len(ids)) % 251
+        self.logits = np.linspace(-1, 1, self.spec.vocab_size, dtype=np.float32)
+        return 42
+
+    def get_logits(self, n):
+        return self.logits[None]
+
+    def prefix_adopt(self, n_tokens, logits):
+        self.adopted = (n_tokens, logits.copy())
+        return 1048576
+
+    def prefix_kv_region(self, pid):
+        return self.kv.ctypes.data, self.kv.size
+
+
+def _replica_worker(rank, world, port, q):
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import advspec_loader
+
+    advspec_loader.load()
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from advspec_b200 import runtime
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    e = _FakeEngine(64, 4096)
+    alias = lambda ptr, n: torch.from_numpy(e.kv)  # noqa: E731  (host memory instead of a device pointer)
+    pid = runtime.replicate_prefix(e, list(range(37)), rank, src=0, alias=alias)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, pid, int(e.kv.astype(np.int64).sum()), None if e.adopted is None else (e.adopted[0], float(e.adopted[1].sum()))))
+
+
+def test_replica_prefix_broadcast_world2():
+    """Rank 0 prefills once; rank 1 adopts the broadcast KV bytes and logits instead of recomputing."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_replica_worker, args=(r, 2, 29633, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    (r0, pid0, sum0, ad0), (r1, pid1, sum1, ad1) = got
+    assert pid0 == 42 and pid1 == 1048576
+    assert sum0 == sum1 and sum0 > 0, "rank 1 must hold rank 0's KV bytes"
+    assert ad0 is None and ad1[0] == 37 and abs(ad1[1]) < 1e-3
