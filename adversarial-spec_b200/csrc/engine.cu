@@ -172,6 +172,8 @@ cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   return cudaGetLastError();
 }
 
+bool g_gemm_narrow = false;  // ADVSPEC_GEMM_NARROW=1 (experiment)
+
 // C = A[M,K] * B[N,K]^T on tcgen05.  A rows / B rows are the TMA extents.
 cudaError_t launch_gemm(const void* A, int64_t lda, int64_t a_rows, const void* B, int64_t ldb,
                         const GemmParams& p, int epi, int device, cudaStream_t st, std::string* err) {
@@ -184,7 +186,7 @@ cudaError_t launch_gemm(const void* A, int64_t lda, int64_t a_rows, const void* 
   // pick the BN in {128, 256} with the smaller waves x BN product (wave quantisation costs up to 14 %
   // on the N = 4096 / 6144 matrices with BN = 256).
   bool wide = p.N > 128;
-  if (wide) {
+  if (wide && g_gemm_narrow) {  // ADVSPEC_GEMM_NARROW=1; measured SLOWER in round 1 (prefill 94 -> 103 ms), off by default
     const int sms = num_sms(device);
     const int64_t mt = (p.M + kGemmBM - 1) / kGemmBM;
     const int64_t t256 = mt * ((p.N + 255) / 256), t128 = mt * ((p.N + 127) / 128);
@@ -1007,6 +1009,7 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   if (const char* gi = getenv("ADVSPEC_GEMV_IMPL")) g_gemv_impl = std::max(1, std::min(3, atoi(gi)));
   if (const char* ai = getenv("ADVSPEC_ATTN_IMPL")) g_attn_impl = atoi(ai) == 1 ? 1 : 2;
   if (const char* xm = getenv("ADVSPEC_X_SMEM_MAX")) g_x_smem_max = (size_t)atoll(xm);
+  g_gemm_narrow = getenv("ADVSPEC_GEMM_NARROW") != nullptr;
   if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
 
   auto boot = [&]() -> advspec_status {
@@ -1698,6 +1701,7 @@ advspec_status advspec_op_gemv(int32_t device, const void* W, const void* x, con
   if (const char* gi = getenv("ADVSPEC_GEMV_IMPL")) g_gemv_impl = std::max(1, std::min(3, atoi(gi)));
   if (const char* ai = getenv("ADVSPEC_ATTN_IMPL")) g_attn_impl = atoi(ai) == 1 ? 1 : 2;
   if (const char* xm = getenv("ADVSPEC_X_SMEM_MAX")) g_x_smem_max = (size_t)atoll(xm);
+  g_gemm_narrow = getenv("ADVSPEC_GEMM_NARROW") != nullptr;
   if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
   cudaError_t r = launch_gemv(p, b, device, 0, false);
   if (r != cudaSuccess) {

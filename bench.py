@@ -373,7 +373,7 @@ def run_b200_arm(args, rank, world, local_rank):
                          "frac": gemv_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"],
                          "algorithmic_bytes_per_step": gemv_bytes,
                          "launches_per_step": tl.get("gemv_launches_per_step"),
-                         "kernel_ms_per_step": gemv_ms, "traffic": None,
+                         "kernel_ms_per_step": gemv_ms, "traffic": _ncu_traffic_per_step(spec),
                          "how": "device global-timer stamps at kernel entry inside the graph replay; cost = run + launch gap",
                          "timeline": {k: round(v["us_each"], 2) for k, v in tl.get("rows", {}).items()}},
             "decode": {"ms_per_step": step_ms, "batch": args.opponents, "algorithmic_bytes_per_step": step_bytes,
@@ -402,6 +402,17 @@ def run_b200_arm(args, rank, world, local_rank):
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def _ncu_traffic_per_step(spec):
+    """DRAM bytes per decode step of the GEMV launches, from the committed ncu --set full capture
+    (profiles/r01_gemv_traffic.json: read + write per launch for the four per-layer shapes); lm_head is
+    taken at its algorithmic size.  None when the capture does not match the model."""
+    p = ROOT / "profiles" / "r01_gemv_traffic.json"
+    if not p.exists() or spec.name != "llama-3-8b":
+        return None
+    d = json.loads(p.read_text())
+    return (d["per_layer_traffic_mb"] * spec.n_layers + spec.vocab_size * spec.d_model * 2 / 1e6) * 1e6
 
 
 def _prompt_ids(spec, system_prompt, user_message):
