@@ -99,6 +99,7 @@ REGISTRY: dict[str, ModelSpec] = {
         _llama("tiny-llama-128", 2, 512, 4, 2, 1024, 2048, head_dim=128),
         _llama("tiny-qwen2", 2, 256, 4, 2, 512, 1024, head_dim=64, family="qwen2", qkv_bias=True,
                theta=1000000.0, eps=1e-6),
+        _llama("tiny-gqa4", 2, 512, 8, 2, 768, 1024, head_dim=64),
         _llama("tiny-phi3", 2, 192, 2, 2, 512, 1024, head_dim=96, family="phi3", theta=10000.0),
         _llama("tiny-gemma256", 2, 512, 2, 2, 512, 1024, head_dim=256, family="gemma", act=1,
                tied_lm_head=True, embed_scale=math.sqrt(512.0), theta=10000.0, eps=1e-6),

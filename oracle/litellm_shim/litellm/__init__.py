@@ -46,6 +46,20 @@ def _get_model(name: str):
     from oracle import hf_oracle
 
     with _models_mu:
+        if name not in _models and "gpt2" in name.lower():
+            # BASELINE configs[0]: the CPU-only plumbing case, GPT-2 124M random-init (no engine involved);
+            # n_positions is enlarged so the prompt envelope + stub spec + generation fit
+            import transformers as tf
+            from types import SimpleNamespace
+
+            torch.manual_seed(int(os.environ.get("ADVSPEC_WEIGHT_SEED", "0")))
+            cfg = tf.GPT2Config(n_positions=4096)
+            model = tf.AutoModelForCausalLM.from_config(cfg).float().eval()
+            for layer in model.transformer.h:
+                layer.register_forward_pre_hook(_pre_hook)
+                layer.register_forward_hook(_post_hook)
+            _models[name] = (SimpleNamespace(n_layers=cfg.n_layer, vocab_size=cfg.vocab_size), model,
+                             SyntheticTokenizer(cfg.vocab_size))
         if name not in _models:
             spec = resolve(name)
             seed = int(os.environ.get("ADVSPEC_WEIGHT_SEED", "0"))

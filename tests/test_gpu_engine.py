@@ -241,3 +241,43 @@ def test_full_size_properties_llama3_8b(cuda_device, diag):
     tm = e.timing()
     diag["full_size/prefill_ms_4736"] = tm.prefill_ms
     e.close()
+
+
+@pytest.mark.parametrize("name", ["tiny-gqa4", "tiny-llama"])
+def test_eight_opponents_teacher_forced(cuda_device, diag, name):
+    """The full batch (max_seqs = 8): with G = 4 the opponents fall into two 16-row MMA groups per KV
+    head, with G = 2 into one; every opponent gets its own continuation and must match the oracle."""
+    spec, model, e = make_engine(name, 17)
+    prompt = _tokens(spec, 130, 6)
+    conts = [_tokens(spec, 3, 40 + i) for i in range(8)]
+    pid = e.prefill(prompt)
+    ids = e.fork(pid, list(range(1, 9)))
+    refs = [hf_oracle.hf_logits(model, prompt + c) for c in conts]
+    worst = (0.0, 0.0)
+    for t in range(3):
+        e.decode_step(ids, [c[t] for c in conts])
+        lg = e.get_logits(8)
+        for i in range(8):
+            m2, r2 = rel_errors(lg[i], refs[i][len(prompt) + t])
+            worst = (max(worst[0], m2), max(worst[1], r2))
+    diag[f"eight_opponents/{name}"] = {"max": worst[0], "rms": worst[1]}
+    e.close()
+    assert worst[0] < TOL_MAX and worst[1] < TOL_RMS, worst
+
+
+def test_eos_stops_one_opponent_only(cuda_device):
+    spec, model, e = make_engine("tiny-llama", 9)
+    prompt = _tokens(spec, 50, 2)
+    seeds = [5, 6, 7]
+    pid = e.prefill(prompt)
+    free = e.decode(e.fork(pid, seeds), 10, temperature=0.7)
+    eos = free.tokens[0][3]
+    want = []
+    for toks in free.tokens:  # an opponent stops right after its first eos
+        cut = toks.index(eos) + 1 if eos in toks else len(toks)
+        want.append(toks[:cut])
+    pid = e.prefill(prompt)
+    got = e.decode(e.fork(pid, seeds), 10, temperature=0.7, eos_id=eos)
+    e.close()
+    assert got.tokens == want and got.lens == [len(w) for w in want]
+    assert got.lens[0] <= 4
