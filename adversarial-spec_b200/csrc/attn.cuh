@@ -57,12 +57,14 @@ struct AttnPrefillParams {
 };
 
 // ---------------------------------------------------------------- prefill (TC)
-// CTA = 4 warps x 16 query rows = 64 queries of one head; keys in tiles of 64,
+// CTA = BM/16 warps x 16 query rows = BM queries of one head (BM = 128 halves the K/V re-reads
+// from L2 at long prompts); keys in tiles of 64,
 // double-buffered with cp.async; smem rows are 16-byte-chunk XOR swizzled so
 // ldmatrix is conflict-free.
-template <int DH>
-__global__ void __launch_bounds__(128) attn_prefill_kernel(AttnPrefillParams p) {
-  constexpr int BM = 64, BN = 64;
+template <int DH, int BM>
+__global__ void __launch_bounds__(BM * 2) attn_prefill_kernel(AttnPrefillParams p) {
+  constexpr int BN = 64;
+  constexpr int NT = BM * 2;  // one warp per 16 query rows
   constexpr int CPR = DH / 8;  // 16-byte chunks per row
   extern __shared__ __align__(128) uint8_t attn_smem[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(attn_smem);
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(AttnPrefillParams p) 
   auto swz = [](int row, int chunk) { return row * DH + ((chunk ^ (row & 7)) << 3); };
 
   // Q tile
-  for (int id = tid; id < BM * CPR; id += 128) {
+  for (int id = tid; id < BM * CPR; id += NT) {
     const int r = id / CPR, c = id % CPR;
     const bool ok = (q0 + r) < p.n_q;
     const __nv_bfloat16* src = p.q + (int64_t)(ok ? q0 + r : 0) * p.ldq + h * DH + c * 8;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(AttnPrefillParams p) 
   }
   auto load_kv = [&](int tile, int buf) {
     const int k0 = tile * BN;
-    for (int id = tid; id < BN * CPR; id += 128) {
+    for (int id = tid; id < BN * CPR; id += NT) {
       const int r = id / CPR, c = id % CPR;
       const bool ok = (k0 + r) < total_kv;
       const int64_t off = (int64_t)(ok ? k0 + r : 0) * DH + c * 8;

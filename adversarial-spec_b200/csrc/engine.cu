@@ -31,6 +31,7 @@
 
 #include "attn.cuh"
 #include "attn_decode_mma.cuh"
+#include "attn_prefill_tc.cuh"
 #include "common.cuh"
 #include "decode_kernels.cuh"
 #include "gemm_tcgen05.cuh"
@@ -173,6 +174,7 @@ cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
 }
 
 bool g_gemm_narrow = false;  // ADVSPEC_GEMM_NARROW=1 (experiment)
+bool g_attn_prefill_tc = true;  // ADVSPEC_ATTN_PREFILL_TC=0 falls back to the mma.sync kernel (A/B)
 
 // C = A[M,K] * B[N,K]^T on tcgen05.  A rows / B rows are the TMA extents.
 cudaError_t launch_gemm(const void* A, int64_t lda, int64_t a_rows, const void* B, int64_t ldb,
@@ -385,27 +387,43 @@ cudaError_t launch_attn_prefill(const AttnPrefillParams& p, int DH, int impl, cu
     attn_prefill_check_kernel<<<grid, 256, 0, st>>>(p, DH);
     return cudaGetLastError();
   }
-  dim3 grid((p.n_q + 63) / 64, p.H);
-  if (DH == 128) {
-    static bool done = false;
-    const int smem = (64 + 4 * 64) * 128 * 2;
-    if (!done) {
-      cudaError_t e = set_smem(attn_prefill_kernel<128>, smem);
-      if (e != cudaSuccess) return e;
-      done = true;
-    }
-    attn_prefill_kernel<128><<<grid, 128, smem, st>>>(p);
-  } else {
-    static bool done = false;
-    const int smem = (64 + 4 * 64) * 64 * 2;
-    if (!done) {
-      cudaError_t e = set_smem(attn_prefill_kernel<64>, smem);
-      if (e != cudaSuccess) return e;
-      done = true;
-    }
-    attn_prefill_kernel<64><<<grid, 128, smem, st>>>(p);
-  }
+  const bool big = p.n_q >= 512;  // 128-row query tiles once there are enough tiles to fill the GPU
+  auto launch = [&](auto kern, int bm) -> cudaError_t {
+    const int smem = (bm + 4 * 64) * DH * 2;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((p.n_q + bm - 1) / bm, p.H);
+    kern<<<grid, bm * 2, smem, st>>>(p);
+    return cudaSuccess;
+  };
+  cudaError_t le;
+  if (DH == 128) le = big ? launch(attn_prefill_kernel<128, 128>, 128) : launch(attn_prefill_kernel<128, 64>, 64);
+  else le = big ? launch(attn_prefill_kernel<64, 128>, 128) : launch(attn_prefill_kernel<64, 64>, 64);
+  if (le != cudaSuccess) return le;
   (void)err;
+  return cudaGetLastError();
+}
+
+// Prompt attention on tcgen05 (head_dim 128): Q from [n_q][ldq] rows, K/V from [Hkv*kv_stride][128] rows.
+cudaError_t launch_attn_prefill_tc(const void* q, int64_t ldq, const void* kc, const void* vc, int64_t kv_stride,
+                                   void* out, int n_q, int q_pos0, int H, int Hkv, cudaStream_t st, std::string* err) {
+  CUtensorMap tq, tk, tv;
+  const int64_t kv_rows = (int64_t)Hkv * kv_stride;
+  if (!make_tmap(&tq, q, n_q, (int64_t)H * 128, ldq, 128) || !make_tmap(&tk, kc, kv_rows, 128, 128, 128) ||
+      !make_tmap(&tv, vc, kv_rows, 128, 128, 128)) {
+    if (err) *err = "cuTensorMapEncodeTiled failed (attention)";
+    return cudaErrorInvalidValue;
+  }
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = set_smem(attn_prefill_tc_kernel, kAtSmem);
+    if (e != cudaSuccess) return e;
+    done = true;
+  }
+  AttnPrefillTcParams p{reinterpret_cast<__nv_bfloat16*>(out), n_q, q_pos0, H, Hkv, (int)kv_stride,
+                        1.0f / sqrtf(128.0f)};
+  dim3 grid((n_q + kAtBM - 1) / kAtBM, H);
+  attn_prefill_tc_kernel<<<grid, kAtThreads, kAtSmem, st>>>(tq, tk, tv, p);
   return cudaGetLastError();
 }
 
@@ -638,7 +656,17 @@ advspec_status prefill_chunk(advspec_engine* e, int m, int pos0) {
     E_CUDA(e, cudaGetLastError());
     AttnPrefillParams ap{e->p_qkv, QKV, prefix_k(e, l), prefix_v(e, l), d.max_prefix_tokens, e->p_attn,
                          m, pos0, d.n_heads, d.n_kv_heads, 1.0f / sqrtf((float)d.head_dim)};
-    E_CUDA(e, launch_attn_prefill(ap, d.head_dim, (e->debug_flags & 2) ? 1 : 0, e->stream, nullptr));
+    if (d.head_dim == 128 && g_attn_prefill_tc && !(e->debug_flags & 2)) {
+      std::string why;
+      cudaError_t r = launch_attn_prefill_tc(e->p_qkv, QKV, prefix_k(e, l), prefix_v(e, l), d.max_prefix_tokens,
+                                             e->p_attn, m, pos0, d.n_heads, d.n_kv_heads, e->stream, &why);
+      if (r != cudaSuccess) {
+        e->fail("tcgen05 attention launch failed: %s %s", cudaGetErrorString(r), why.c_str());
+        return ADVSPEC_ERR_CUDA;
+      }
+    } else {
+      E_CUDA(e, launch_attn_prefill(ap, d.head_dim, (e->debug_flags & 2) ? 1 : 0, e->stream, nullptr));
+    }
     s = prefill_gemm(e, e->p_attn, HD, w.wo, HD, e->p_x, dm, nullptr, m, dm, HD, EPI_RESADD_F32);
     if (s) return s;
     rmsnorm_kernel<<<m, 256, 0, e->stream>>>(e->p_x, w.mlp_norm, e->p_xn, dm, d.norm_eps);
@@ -1010,6 +1038,7 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   if (const char* ai = getenv("ADVSPEC_ATTN_IMPL")) g_attn_impl = atoi(ai) == 1 ? 1 : 2;
   if (const char* xm = getenv("ADVSPEC_X_SMEM_MAX")) g_x_smem_max = (size_t)atoll(xm);
   g_gemm_narrow = getenv("ADVSPEC_GEMM_NARROW") != nullptr;
+  if (const char* tc = getenv("ADVSPEC_ATTN_PREFILL_TC")) g_attn_prefill_tc = atoi(tc) != 0;
   if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
 
   auto boot = [&]() -> advspec_status {
@@ -1028,6 +1057,9 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     e->skv_layer_elems = (size_t)d.max_seqs * d.n_kv_heads * d.max_new_tokens * d.head_dim;
     E_CUDA(e, dmalloc(&e->pkv, (size_t)d.n_layers * 2 * e->pkv_layer_elems));
     E_CUDA(e, dmalloc(&e->skv, (size_t)d.n_layers * 2 * e->skv_layer_elems));
+    // whole 64/128-key boxes are loaded by TMA: rows never written must hold finite values (0 * NaN = NaN)
+    E_CUDA(e, cudaMemsetAsync(e->pkv, 0, (size_t)d.n_layers * 2 * e->pkv_layer_elems * sizeof(__nv_bfloat16), e->stream));
+    E_CUDA(e, cudaMemsetAsync(e->skv, 0, (size_t)d.n_layers * 2 * e->skv_layer_elems * sizeof(__nv_bfloat16), e->stream));
     e->C = std::min(4096, (d.max_prefix_tokens + 127) / 128 * 128);
     if (const char* pc = getenv("ADVSPEC_PREFILL_CHUNK"))  // tests: force multi-chunk prefill on small prompts
       e->C = std::max(128, std::min(e->C, atoi(pc) / 128 * 128));
@@ -1702,6 +1734,7 @@ advspec_status advspec_op_gemv(int32_t device, const void* W, const void* x, con
   if (const char* ai = getenv("ADVSPEC_ATTN_IMPL")) g_attn_impl = atoi(ai) == 1 ? 1 : 2;
   if (const char* xm = getenv("ADVSPEC_X_SMEM_MAX")) g_x_smem_max = (size_t)atoll(xm);
   g_gemm_narrow = getenv("ADVSPEC_GEMM_NARROW") != nullptr;
+  if (const char* tc = getenv("ADVSPEC_ATTN_PREFILL_TC")) g_attn_prefill_tc = atoi(tc) != 0;
   if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
   cudaError_t r = launch_gemv(p, b, device, 0, false);
   if (r != cudaSuccess) {
@@ -1722,7 +1755,17 @@ advspec_status advspec_op_attn_prefill(int32_t device, const void* q, int64_t ld
                       reinterpret_cast<const __nv_bfloat16*>(vcache), kv_stride,
                       reinterpret_cast<__nv_bfloat16*>(out), n_q, q_pos0, n_heads, n_kv_heads,
                       1.0f / sqrtf((float)head_dim)};
-  cudaError_t r = launch_attn_prefill(p, head_dim, impl, 0, nullptr);
+  cudaError_t r;
+  if (impl == 2) {
+    if (head_dim != 128) {
+      g_create_error = "op_attn_prefill: the tcgen05 kernel serves head_dim 128 only";
+      return ADVSPEC_ERR_INVALID;
+    }
+    std::string why;
+    r = launch_attn_prefill_tc(q, ldq, kcache, vcache, kv_stride, out, n_q, q_pos0, n_heads, n_kv_heads, 0, &why);
+  } else {
+    r = launch_attn_prefill(p, head_dim, impl, 0, nullptr);
+  }
   if (r != cudaSuccess) {
     g_create_error = std::string("op_attn_prefill launch: ") + cudaGetErrorString(r);
     return ADVSPEC_ERR_CUDA;
