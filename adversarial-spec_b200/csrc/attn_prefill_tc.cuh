@@ -2,12 +2,13 @@
 //
 // One CTA = 128 query rows of one head; keys in tiles of 128.  Per tile
 //   S = Q K^T   tcgen05.mma 128x128x128, Q and K K-major from TMA-swizzled shared memory, S in TMEM
-//   softmax     4 warps, ONE THREAD PER QUERY ROW: tcgen05.ld its 128 scores, mask, exp2 against a
+//   softmax     8 warps, TWO THREADS PER QUERY ROW (64 keys each; the exponentials are MUFU-bound, so the
+//               row is split): tcgen05.ld the scores, mask, exp2 against a
 //               lazily-updated row maximum (rescale O only when the maximum grew by > 2^8), write P
 //               (bf16) back to shared memory in the 128B-swizzled K-major layout
 //   O += P V    tcgen05.mma 128x128x128, A = P (K-major), B = V straight from its [key][dim] tile as an
 //               MN-major operand; O accumulates in TMEM across all tiles
-// Warp roles: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 softmax/epilogue.
+// Warp roles: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-9 softmax/epilogue.
 // S is double-buffered in TMEM so QK^T of tile j+1 runs under the softmax of tile j.
 // TMEM columns: S0 [0,128) S1 [128,256) O [256,384).  head_dim 128 only (64/96/256 use attn.cuh).
 #pragma once
@@ -22,7 +23,7 @@ constexpr int kAtStages = 2;
 constexpr int kAtHalf = 128 * 64 * 2;               // bytes of a [128 rows][64 elems] half tile (16 KB)
 constexpr int kAtTile = 2 * kAtHalf;                // 32 KB: Q, K, V or P tile
 constexpr int kAtSmem = kAtTile * (2 + 2 * kAtStages) + 256 + 1024;  // Q, P, K/V stages, barriers, alignment
-constexpr int kAtThreads = 192;
+constexpr int kAtThreads = 320;  // TMA warp, MMA warp, 8 softmax warps (2 threads per query row)
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -77,6 +78,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint64_t* p_full = s_empty + 2;          // 1
   uint64_t* pv_done = p_full + 1;          // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  __shared__ float s_mx[2][2][128];  // [tile parity][column half][row]: row-maximum exchange between the two threads of a row
+  __shared__ float s_lsum[2][128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qtiles = (p.n_q + kAtBM - 1) / kAtBM;
@@ -99,9 +102,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 128);
+      mbar_init(&s_empty[s], 256);
     }
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -168,33 +171,39 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   } else if (warp >= 2) {
     // ------------------------------ softmax + epilogue ------------------------
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int ch = (warp - 2) >> 2;       // which 64-key half of the row this thread handles
     const int row = quad * 32 + lane;     // query row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const uint32_t col_off = (uint32_t)(ch * 64);
     const int qpos = p.q_pos0 + q0 + row;
     const float sl2 = p.scale * 1.4426950408889634f;
     float m_used = -INFINITY;  // row maximum the exponentials are currently taken against (raw score units)
-    float l_run = 0.f;
+    float l_run = 0.f;         // this thread's share of the row sum
     for (int j = 0; j < n_t; ++j) {
       const int b = j & 1;
       mbar_wait(&s_full[b], ((uint32_t)(j >> 1)) & 1u, 0xB00u + b);
       tc_fence_after();
-      uint32_t sv[128];
+      uint32_t sv[64];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS[b] + lane_off + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+      for (int c = 0; c < 2; ++c)
+        tmem_ld_32x32(tS[b] + lane_off + col_off + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_empty[b]);
       // mask (causal and past-the-end keys) and row maximum
-      const int k0 = j * kAtBN;
-      const bool need_mask = (k0 + kAtBN - 1 > p.q_pos0 + q0) || (k0 + kAtBN > total_kv);
+      const int k0 = j * kAtBN + ch * 64;
+      const bool need_mask = (j * kAtBN + kAtBN - 1 > p.q_pos0 + q0) || (j * kAtBN + kAtBN > total_kv);
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 128; ++c) {
+      for (int c = 0; c < 64; ++c) {
         float v = __uint_as_float(sv[c]);
         if (need_mask && (k0 + c > qpos || k0 + c >= total_kv)) v = -INFINITY;
         sv[c] = __float_as_uint(v);
         mx = fmaxf(mx, v);
       }
+      s_mx[b][ch][row] = mx;
+      named_bar_sync(2, 256);
+      mx = fmaxf(mx, s_mx[b][ch ^ 1][row]);
       // P smem and the O accumulator are only touched once the previous tile's P V has retired
       if (j > 0) mbar_wait(pv_done, ((uint32_t)(j - 1)) & 1u, 0xB10u);
       // lazy rescale: keep exponentiating against m_used until the row maximum has grown by > 2^8
@@ -206,13 +215,13 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (j > 0) {
           tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             uint32_t ov[32];
-            tmem_ld_32x32(tO + lane_off + (uint32_t)(c * 32), ov);
+            tmem_ld_32x32(tO + lane_off + col_off + (uint32_t)(c * 32), ov);
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * corr);
-            tmem_st_32x32(tO + lane_off + (uint32_t)(c * 32), ov);
+            tmem_st_32x32(tO + lane_off + col_off + (uint32_t)(c * 32), ov);
           }
           tmem_st_wait();
         }
@@ -220,9 +229,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       const float m_off = (m_used == -INFINITY) ? 0.f : m_used * sl2;
       float rs = 0.f;
-      uint8_t* prow = sP + (size_t)row * 128;
+      uint8_t* prow = sP + (size_t)ch * kAtHalf + (size_t)row * 128;  // keys [ch*64, ch*64+64) = P half `ch`
 #pragma unroll
-      for (int c8 = 0; c8 < 16; ++c8) {  // 16-byte chunks of 8 keys
+      for (int c8 = 0; c8 < 8; ++c8) {  // 16-byte chunks of 8 keys
         float pv[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -234,24 +243,27 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         o.y = pack_bf16(pv[2], pv[3]);
         o.z = pack_bf16(pv[4], pv[5]);
         o.w = pack_bf16(pv[6], pv[7]);
-        *reinterpret_cast<uint4*>(prow + (c8 >> 3) * kAtHalf + (((c8 & 7) ^ (row & 7)) << 4)) = o;
+        *reinterpret_cast<uint4*>(prow + ((c8 ^ (row & 7)) << 4)) = o;
       }
       l_run += rs;
       fence_proxy_async();  // P was written by the generic proxy; the MMA reads it through the async proxy
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // ---- epilogue: O / l -> bf16 -> global (each thread owns one 256-byte output row)
+    // ---- epilogue: O / l -> bf16 -> global (two threads share one 256-byte output row)
+    s_lsum[ch][row] = l_run;
+    named_bar_sync(2, 256);
+    const float l_tot = s_lsum[0][row] + s_lsum[1][row];
     mbar_wait(pv_done, ((uint32_t)(n_t - 1)) & 1u, 0xB20u);
     tc_fence_after();
-    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
     const int qr = q0 + row;
-    __nv_bfloat16* dst = p.out + (int64_t)qr * (p.H * kAtDH) + h * kAtDH;
+    __nv_bfloat16* dst = p.out + (int64_t)qr * (p.H * kAtDH) + h * kAtDH + ch * 64;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t ov[32];
       __syncwarp();
-      tmem_ld_32x32(tO + lane_off + (uint32_t)(c * 32), ov);
+      tmem_ld_32x32(tO + lane_off + col_off + (uint32_t)(c * 32), ov);
       tmem_ld_wait();
       if (qr < p.n_q) {
 #pragma unroll

@@ -1060,7 +1060,8 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     // whole 64/128-key boxes are loaded by TMA: rows never written must hold finite values (0 * NaN = NaN)
     E_CUDA(e, cudaMemsetAsync(e->pkv, 0, (size_t)d.n_layers * 2 * e->pkv_layer_elems * sizeof(__nv_bfloat16), e->stream));
     E_CUDA(e, cudaMemsetAsync(e->skv, 0, (size_t)d.n_layers * 2 * e->skv_layer_elems * sizeof(__nv_bfloat16), e->stream));
-    e->C = std::min(4096, (d.max_prefix_tokens + 127) / 128 * 128);
+    // prefill chunk: up to 8192 tokens per pass (fewer, fuller waves of GEMM tiles than 4096 + remainder)
+    e->C = std::min(8192, (d.max_prefix_tokens + 127) / 128 * 128);
     if (const char* pc = getenv("ADVSPEC_PREFILL_CHUNK"))  // tests: force multi-chunk prefill on small prompts
       e->C = std::max(128, std::min(e->C, atoi(pc) / 128 * 128));
     const size_t C = e->C, dm = d.d_model, QKV = qkv_dim(d), HD = (size_t)d.n_heads * d.head_dim;
