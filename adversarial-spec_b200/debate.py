@@ -25,12 +25,15 @@ if __package__ in (None, ""):  # executed as a script: make the hyphenated packa
 
     advspec_loader.load()
     from advspec_b200 import models as _models, providers as _providers, session as _session
-    from advspec_b200.envelope import get_doc_type_name
+    from advspec_b200.envelope import EXPORT_TASKS_PROMPT, get_doc_type_name
 else:
     from . import models as _models, providers as _providers, session as _session
-    from .envelope import get_doc_type_name
+    from .envelope import EXPORT_TASKS_PROMPT, get_doc_type_name
 
 call_models_parallel = _models.call_models_parallel  # tests patch ``debate.call_models_parallel``
+completion = _models.completion  # second call site of the reference (debate.py:715, export-tasks)
+extract_tasks = _models.extract_tasks
+is_o_series_model = _models.is_o_series_model
 cost_tracker = _models.cost_tracker
 load_context_files = _models.load_context_files
 SessionState = _session.SessionState
@@ -211,10 +214,44 @@ def output_results(args, results, models: list[str], all_agreed: bool, user_feed
         print(cost_tracker.summary())
 
 
+def handle_export_tasks(args, models: list[str]) -> None:
+    """`export-tasks`: the other `completion` call site (reference debate.py:688-736) — one model, one user
+    message, max_tokens 8000, temperature 0.3, no retry; a local b200/ model runs on the same engine."""
+    spec = sys.stdin.read().strip()
+    if not spec:
+        print("Error: No spec provided via stdin", file=sys.stderr)
+        sys.exit(1)
+    prompt = EXPORT_TASKS_PROMPT.format(doc_type_name=get_doc_type_name(args.doc_type), spec=spec)
+    try:
+        kwargs = {"model": models[0], "messages": [{"role": "user", "content": prompt}], "max_tokens": 8000}
+        if not is_o_series_model(models[0]):
+            kwargs["temperature"] = 0.3
+        tasks = extract_tasks(completion(**kwargs).choices[0].message.content)
+        if args.json:
+            print(json.dumps({"tasks": tasks}, indent=2))
+            return
+        print(f"\n=== Extracted {len(tasks)} Tasks ===\n")
+        for i, task in enumerate(tasks, 1):
+            print(f"{i}. [{task.get('type', 'task')}] [{task.get('priority', 'medium')}] {task.get('title', 'Untitled')}")
+            if task.get("description"):
+                print(f"   {task['description'][:100]}...")
+            if task.get("acceptance_criteria"):
+                print(f"   Acceptance criteria: {len(task['acceptance_criteria'])} items")
+            print()
+    except Exception as e:
+        print(f"Error: {e}", file=sys.stderr)
+        sys.exit(1)
+
+
 def main() -> None:
     args = create_parser().parse_args()
     if args.action == "providers":
         _providers.list_providers()
+        return
+    if args.action == "export-tasks":
+        models = parse_models(args)
+        validate_models_before_run(models, False)
+        handle_export_tasks(args, models)
         return
     if args.action != "critique":
         print(f"Error: '{args.action}' is outside the local engine's scope (it is config or a single remote "

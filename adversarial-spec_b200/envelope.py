@@ -69,6 +69,25 @@ Before answering [AGREE] you must: say that you have read every section; list at
 
 If this second pass turns up a problem, give your critique instead. If you still agree, output your verification, then [AGREE] on its own line, then the final document between [SPEC] and [/SPEC] tags."""
 
+EXPORT_TASKS_PROMPT = """Read this {doc_type_name} and turn it into a list of actionable tasks.
+
+Document:
+{spec}
+
+Write every task in exactly this format:
+[TASK]
+title: <short task title>
+type: <user-story | bug | task | spike>
+priority: <high | medium | low>
+description: <what has to be done>
+acceptance_criteria:
+- <criterion 1>
+- <criterion 2>
+[/TASK]
+
+Cover user stories, technical requirements, risks (as spikes) and non-functional requirements. Every
+actionable statement in the document should end up in some task."""
+
 PRESERVE_INTENT_PROMPT = """**PRESERVE THE AUTHOR'S INTENT**
 Treat every existing requirement as deliberate. Do not delete or substantially rewrite content unless you quote it, state the concrete harm it causes, and show that your change fixes that harm. Prefer adding or clarifying over removing. List every removal separately with its justification."""
 
@@ -133,6 +152,7 @@ if _ref is not None:
     PERSONAS = _ref.PERSONAS
     PRESERVE_INTENT_PROMPT = _ref.PRESERVE_INTENT_PROMPT
     PRESS_PROMPT_TEMPLATE = _ref.PRESS_PROMPT_TEMPLATE
+    EXPORT_TASKS_PROMPT = _ref.EXPORT_TASKS_PROMPT
     REVIEW_PROMPT_TEMPLATE = _ref.REVIEW_PROMPT_TEMPLATE
     get_system_prompt = _ref.get_system_prompt
     get_doc_type_name = _ref.get_doc_type_name

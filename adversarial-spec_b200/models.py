@@ -108,6 +108,43 @@ def extract_spec(response: str) -> Optional[str]:
     return response[start: response.find("[/SPEC]")].strip()
 
 
+_TASK_KEYS = ("title:", "type:", "priority:", "description:", "acceptance_criteria:")
+
+
+def extract_tasks(response: str) -> list[dict]:
+    """[TASK]...[/TASK] blocks -> dicts (reference parser: models.py:163-247, quirks included: a key line
+    closes the previous field; a field with several lines is joined with newlines; acceptance_criteria is
+    a list only when it is the last field of the block; blocks without a title are dropped)."""
+
+    def close(values: list[str]):
+        return "\n".join(values).strip() if len(values) > 1 else (values[0] if values else "")
+
+    tasks = []
+    for block in response.split("[TASK]")[1:]:
+        if "[/TASK]" not in block:
+            continue
+        task: dict = {}
+        key: Optional[str] = None
+        values: list[str] = []
+        for raw in block.split("[/TASK]")[0].strip().split("\n"):
+            line = raw.strip()
+            head = next((k for k in _TASK_KEYS if line.startswith(k)), None)
+            if head is not None:
+                if key:
+                    task[key] = close(values)
+                key = head[:-1]
+                values = [] if key == "acceptance_criteria" else [line[len(head):].strip()]
+            elif line.startswith("- ") and key == "acceptance_criteria":
+                values.append(line[2:])
+            elif key:
+                values.append(line)
+        if key:
+            task[key] = values if key == "acceptance_criteria" else "\n".join(values).strip()
+        if task.get("title"):
+            tasks.append(task)
+    return tasks
+
+
 def _finish(model: str, content: str, input_tokens: int, output_tokens: int) -> ModelResponse:
     agreed = "[AGREE]" in content
     extracted = extract_spec(content)

@@ -64,6 +64,12 @@ CASES = [
      "responses": {"fake/a": {"content": "x", "in": 1, "out": 1}}},
     {"name": "missing_key_exit2", "argv": ["critique", "--models", "gpt-4o"],
      "responses": {"gpt-4o": {"content": "x", "in": 1, "out": 1}}},
+    {"name": "export_tasks_json", "argv": ["export-tasks", "--models", "fake/a", "--doc-type", "prd", "--json"],
+     "responses": {"fake/a": {"content": "intro\n[TASK]\ntitle: Add login\ntype: user-story\npriority: high\ndescription: Users sign in\nwith email.\nacceptance_criteria:\n- form exists\n- errors shown\n[/TASK]\n[TASK]\ntype: bug\n[/TASK]\n[TASK]\ntitle: Spike cache\nacceptance_criteria:\n- measured\npriority: low\n[/TASK] trailing", "in": 5, "out": 5}}},
+    {"name": "export_tasks_text", "argv": ["export-tasks", "--models", "fake/a"],
+     "responses": {"fake/a": {"content": "[TASK]\ntitle: Rate limit the API\ntype: task\npriority: medium\ndescription: " + "x" * 130 + "\nacceptance_criteria:\n- 429 returned\n[/TASK]", "in": 5, "out": 5}}},
+    {"name": "export_tasks_model_error", "argv": ["export-tasks", "--models", "fake/a"],
+     "responses": {"fake/a": {"raise": "provider down"}}},
     {"name": "press_round_json",
      "argv": ["critique", "--models", "fake/a", "--press", "--json", "--round", "2"],
      "responses": {"fake/a": {"content": "verified [AGREE]\n[SPEC] kept [/SPEC]", "in": 50, "out": 9}}},

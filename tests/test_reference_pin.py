@@ -43,7 +43,8 @@ def test_cli_matches_reference(case, monkeypatch, tmp_path):
     monkeypatch.setattr(models, "cost_tracker", models.CostTracker())
     monkeypatch.setattr(debate, "cost_tracker", models.cost_tracker)
     out, err, rc = io.StringIO(), io.StringIO(), 0
-    with patch.object(models, "completion", _canned(case)), patch.object(models.time, "sleep", lambda s, _real=time.sleep: _real(0.2 * s)), \
+    with patch.object(models, "completion", _canned(case)), patch.object(debate, "completion", _canned(case)), \
+            patch.object(models.time, "sleep", lambda s, _real=time.sleep: _real(0.2 * s)), \
             redirect_stdout(out), redirect_stderr(err):
         try:
             debate.main()
@@ -83,3 +84,30 @@ def test_cost_tracker_math():
 def test_model_response_defaults():
     r = models.ModelResponse(model="m", response="r", agreed=False, spec=None)
     assert (r.error, r.input_tokens, r.output_tokens, r.cost) == (None, 0, 0, 0.0)
+
+
+@pytest.mark.skipif(not Path("/root/reference/skills/adversarial-spec/scripts/models.py").exists(),
+                    reason="reference tree only exists in the build container")
+def test_extract_tasks_agrees_with_reference_on_random_blocks():
+    """Property test in the build container: the restated task parser equals the reference's own
+    function (models.py:163-247) on randomly assembled [TASK] blocks."""
+    import importlib.util
+    import random
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as td:
+        Path(td, "litellm.py").write_text("suppress_debug_info=False\ndef completion(**k):\n    raise RuntimeError\n")
+        sys.path[:0] = [td, "/root/reference/skills/adversarial-spec/scripts"]
+        try:
+            spec = importlib.util.spec_from_file_location("_ref_models", "/root/reference/skills/adversarial-spec/scripts/models.py")
+            ref = importlib.util.module_from_spec(spec)
+            sys.modules["_ref_models"] = ref  # dataclasses resolves the defining module through sys.modules
+            spec.loader.exec_module(ref)
+        finally:
+            del sys.path[:2]
+    rng = random.Random(0)
+    lines = ["title: A", "title:", "type: bug", "priority: high", "description: d1", "more text", "- item", "- ",
+             "acceptance_criteria:", "acceptance_criteria: inline", "  - indented", "", "random: x", "[TASK]", "[/TASK]"]
+    for _ in range(400):
+        txt = "\n".join(rng.choice(lines) for _ in range(rng.randint(0, 25)))
+        assert models.extract_tasks(txt) == ref.extract_tasks(txt), txt
