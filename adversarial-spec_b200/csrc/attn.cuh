@@ -54,6 +54,7 @@ struct AttnPrefillParams {
   __nv_bfloat16* out;  // [n_q][H*DH]
   int n_q, q_pos0, H, Hkv;
   float scale;  // head_dim^-0.5
+  int dh;       // head_dim in GLOBAL memory; the tensor-core kernel's tile width DH >= dh is zero-padded
 };
 
 // ---------------------------------------------------------------- prefill (TC)
@@ -78,8 +79,9 @@ __global__ void __launch_bounds__(BM * 2) attn_prefill_kernel(AttnPrefillParams 
   const int q0 = qt * BM;
   const int h = blockIdx.y;
   const int hk = h / (p.H / p.Hkv);
-  const __nv_bfloat16* kbase = p.kc + (int64_t)hk * p.kv_stride * DH;
-  const __nv_bfloat16* vbase = p.vc + (int64_t)hk * p.kv_stride * DH;
+  const int dhg = p.dh;  // <= DH; chunks past it are zero-filled (Phi-3: 96 inside a 128-wide tile)
+  const __nv_bfloat16* kbase = p.kc + (int64_t)hk * p.kv_stride * dhg;
+  const __nv_bfloat16* vbase = p.vc + (int64_t)hk * p.kv_stride * dhg;
   const int total_kv = p.q_pos0 + p.n_q;
   const int last_q = min(q0 + BM, p.n_q) - 1;
   const int n_kvt = (p.q_pos0 + last_q) / BN + 1;
@@ -89,16 +91,16 @@ __global__ void __launch_bounds__(BM * 2) attn_prefill_kernel(AttnPrefillParams 
   // Q tile
   for (int id = tid; id < BM * CPR; id += NT) {
     const int r = id / CPR, c = id % CPR;
-    const bool ok = (q0 + r) < p.n_q;
-    const __nv_bfloat16* src = p.q + (int64_t)(ok ? q0 + r : 0) * p.ldq + h * DH + c * 8;
+    const bool ok = (q0 + r) < p.n_q && c * 8 < dhg;
+    const __nv_bfloat16* src = p.q + (int64_t)(ok ? q0 + r : 0) * p.ldq + h * dhg + (ok ? c * 8 : 0);
     cp_async16(sQ + swz(r, c), src, ok);
   }
   auto load_kv = [&](int tile, int buf) {
     const int k0 = tile * BN;
     for (int id = tid; id < BN * CPR; id += NT) {
       const int r = id / CPR, c = id % CPR;
-      const bool ok = (k0 + r) < total_kv;
-      const int64_t off = (int64_t)(ok ? k0 + r : 0) * DH + c * 8;
+      const bool ok = (k0 + r) < total_kv && c * 8 < dhg;
+      const int64_t off = (int64_t)(ok ? k0 + r : 0) * dhg + (ok ? c * 8 : 0);
       cp_async16(sK + buf * BN * DH + swz(r, c), kbase + off, ok);
       cp_async16(sV + buf * BN * DH + swz(r, c), vbase + off, ok);
     }
@@ -220,11 +222,13 @@ __global__ void __launch_bounds__(BM * 2) attn_prefill_kernel(AttnPrefillParams 
     const float inv = (l > 0.f) ? 1.0f / l : 0.f;
     const int qr = q0 + warp * 16 + g + i * 8;
     if (qr < p.n_q) {
-      __nv_bfloat16* dst = p.out + (int64_t)qr * (p.H * DH) + h * DH;
+      __nv_bfloat16* dst = p.out + (int64_t)qr * (p.H * dhg) + h * dhg;
 #pragma unroll
       for (int d = 0; d < DH / 8; ++d) {
-        const uint32_t v = pack_bf16(o[d][2 * i] * inv, o[d][2 * i + 1] * inv);
-        *reinterpret_cast<uint32_t*>(dst + d * 8 + 2 * t4) = v;
+        if (d * 8 < dhg) {
+          const uint32_t v = pack_bf16(o[d][2 * i] * inv, o[d][2 * i + 1] * inv);
+          *reinterpret_cast<uint32_t*>(dst + d * 8 + 2 * t4) = v;
+        }
       }
     }
   }

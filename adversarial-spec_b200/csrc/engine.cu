@@ -381,15 +381,15 @@ cudaError_t launch_gemv(const GemvParams& p, int b, int device, cudaStream_t st,
 // -------------------------------------------------------------- attention
 cudaError_t launch_attn_prefill(const AttnPrefillParams& p, int DH, int impl, cudaStream_t st,
                                 std::string* err) {
-  if (impl == 1 || (DH != 64 && DH != 128)) {
+  if (impl == 1 || DH % 8 != 0 || DH > 256) {
     const int64_t warps = (int64_t)p.n_q * p.H;
     const int grid = (int)((warps * 32 + 255) / 256);
     attn_prefill_check_kernel<<<grid, 256, 0, st>>>(p, DH);
     return cudaGetLastError();
   }
   const bool big = p.n_q >= 512;  // 128-row query tiles once there are enough tiles to fill the GPU
-  auto launch = [&](auto kern, int bm) -> cudaError_t {
-    const int smem = (bm + 4 * 64) * DH * 2;
+  auto launch = [&](auto kern, int bm, int dht) -> cudaError_t {
+    const int smem = (bm + 4 * 64) * dht * 2;
     cudaError_t e = set_smem(kern, smem);
     if (e != cudaSuccess) return e;
     dim3 grid((p.n_q + bm - 1) / bm, p.H);
@@ -397,8 +397,9 @@ cudaError_t launch_attn_prefill(const AttnPrefillParams& p, int DH, int impl, cu
     return cudaSuccess;
   };
   cudaError_t le;
-  if (DH == 128) le = big ? launch(attn_prefill_kernel<128, 128>, 128) : launch(attn_prefill_kernel<128, 64>, 64);
-  else le = big ? launch(attn_prefill_kernel<64, 128>, 128) : launch(attn_prefill_kernel<64, 64>, 64);
+  if (DH <= 64) le = big ? launch(attn_prefill_kernel<64, 128>, 128, 64) : launch(attn_prefill_kernel<64, 64>, 64, 64);
+  else if (DH <= 128) le = big ? launch(attn_prefill_kernel<128, 128>, 128, 128) : launch(attn_prefill_kernel<128, 64>, 64, 128);
+  else le = launch(attn_prefill_kernel<256, 64>, 64, 256);  // Gemma: 256-wide heads
   if (le != cudaSuccess) return le;
   (void)err;
   return cudaGetLastError();
@@ -655,7 +656,7 @@ advspec_status prefill_chunk(advspec_engine* e, int m, int pos0) {
                                                    d.n_heads, d.n_kv_heads, d.head_dim);
     E_CUDA(e, cudaGetLastError());
     AttnPrefillParams ap{e->p_qkv, QKV, prefix_k(e, l), prefix_v(e, l), d.max_prefix_tokens, e->p_attn,
-                         m, pos0, d.n_heads, d.n_kv_heads, 1.0f / sqrtf((float)d.head_dim)};
+                         m, pos0, d.n_heads, d.n_kv_heads, 1.0f / sqrtf((float)d.head_dim), d.head_dim};
     if (d.head_dim == 128 && g_attn_prefill_tc && !(e->debug_flags & 2)) {
       std::string why;
       cudaError_t r = launch_attn_prefill_tc(e->p_qkv, QKV, prefix_k(e, l), prefix_v(e, l), d.max_prefix_tokens,
@@ -1755,7 +1756,7 @@ advspec_status advspec_op_attn_prefill(int32_t device, const void* q, int64_t ld
                       reinterpret_cast<const __nv_bfloat16*>(kcache),
                       reinterpret_cast<const __nv_bfloat16*>(vcache), kv_stride,
                       reinterpret_cast<__nv_bfloat16*>(out), n_q, q_pos0, n_heads, n_kv_heads,
-                      1.0f / sqrtf((float)head_dim)};
+                      1.0f / sqrtf((float)head_dim), head_dim};
   cudaError_t r;
   if (impl == 2) {
     if (head_dim != 128) {

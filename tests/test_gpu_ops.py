@@ -123,7 +123,8 @@ def _attn_ref(q, kc, vc, n_q, q_pos0, H, Hkv, Dh):
 
 @pytest.mark.parametrize("cfg", [(64, 0, 4, 2, 64), (200, 0, 4, 2, 128), (333, 100, 8, 2, 128),
                                  (1024, 0, 8, 8, 128), (130, 62, 2, 1, 64), (96, 0, 2, 2, 256),
-                                 (128, 0, 2, 2, 128), (640, 256, 4, 1, 128), (4096, 0, 8, 2, 128)])
+                                 (128, 0, 2, 2, 128), (640, 256, 4, 1, 128), (4096, 0, 8, 2, 128),
+                                 (300, 40, 4, 4, 96), (700, 0, 2, 2, 96), (200, 0, 2, 1, 256)])
 @pytest.mark.parametrize("impl", [0, 1, 2])
 def test_attn_prefill(cuda_device, diag, cfg, impl):
     n_q, q_pos0, H, Hkv, Dh = cfg
