@@ -35,6 +35,7 @@
 #include "common.cuh"
 #include "decode_kernels.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemv_chain.cuh"
 #include "gemv_mma.cuh"
 #include "gemv_stream.cuh"
 
@@ -317,11 +318,11 @@ size_t g_x_smem_max = 40000;  // ADVSPEC_X_SMEM_MAX: larger plain-bf16 inputs ar
 template <int B>
 cudaError_t launch_gemv_mma_t(const GemvParams& p, int device, cudaStream_t st, bool pdl) {
   constexpr int kMaxDyn = 232448 - 9 * 1024;  // 227 KB per CTA minus the kernel's 8.5 KB of static shared memory
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // function attributes are per device
+  if (!attr_done[device & 63]) {
     cudaError_t e = set_smem(gemv_mma_kernel<B>, kMaxDyn);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done[device & 63] = true;
   }
   const size_t xbytes = ((size_t)B * ((size_t)p.K * 2 + 16) + 127) / 128 * 128;
   int x_in_smem = 0;
@@ -338,6 +339,74 @@ cudaError_t launch_gemv_mma_t(const GemvParams& p, int device, cudaStream_t st, 
   const int grid = std::max(1, std::min(num_sms(device), pairs));
   const size_t dyn = (size_t)stages * kGmStageBytes + x_smem;
   return launch_pdl(gemv_mma_kernel<B>, dim3(grid), dim3(kGmThreads), dyn, st, pdl, p, stages, x_in_smem);
+}
+
+int g_chain = 0;  // ADVSPEC_CHAIN=1: o-proj -> gate/up -> down -> next qkv (or lm_head) as phases of one launch
+
+// Fills the per-phase staging decisions; returns false when some phase cannot run in the chain kernel.
+bool chain_plan(ChainParams* cp, int b, size_t* x_smem_out, int* stages_out) {
+  constexpr int kMaxDyn = 232448 - 9 * 1024;
+  size_t x_smem = 0;
+  for (int i = 0; i < cp->n_ph; ++i) {
+    ChainPhase& q = cp->ph[i];
+    if (q.K % 16 != 0) return false;
+    const size_t xbytes = ((size_t)b * ((size_t)q.K * 2 + 16) + 127) / 128 * 128;
+    q.x_in_smem = 0;
+    if (q.in_mode == 1) {
+      x_smem = std::max(x_smem, xbytes);
+    } else if (xbytes + 2 * (size_t)kGmStageBytes <= (size_t)kMaxDyn && xbytes <= g_x_smem_max) {
+      q.x_in_smem = 1;
+      x_smem = std::max(x_smem, xbytes);
+    }
+  }
+  if (x_smem + 2 * (size_t)kGmStageBytes > (size_t)kMaxDyn) return false;
+  *x_smem_out = x_smem;
+  *stages_out = std::min<int>(kGmMaxStages, (int)((kMaxDyn - x_smem) / kGmStageBytes));
+  return true;
+}
+
+template <int B>
+cudaError_t launch_chain_t(const ChainParams& cp, size_t x_smem, int stages, int device, cudaStream_t st, bool pdl) {
+  constexpr int kMaxDyn = 232448 - 9 * 1024;
+  static bool attr_done[64] = {};
+  if (!attr_done[device & 63]) {
+    cudaError_t e = set_smem(gemv_chain_kernel<B>, kMaxDyn);
+    if (e != cudaSuccess) return e;
+    attr_done[device & 63] = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(num_sms(device));  // one CTA per SM, all co-resident (the grid barrier needs it)
+  cfg.blockDim = dim3(kGmThreads);
+  cfg.dynamicSmemBytes = (size_t)stages * kGmStageBytes + x_smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  at[n].id = cudaLaunchAttributeCooperative;
+  at[n].val.cooperative = 1;
+  ++n;
+  if (pdl && g_use_pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, gemv_chain_kernel<B>, cp, stages);
+}
+
+cudaError_t launch_chain(const ChainParams& cp, int b, size_t x_smem, int stages, int device, cudaStream_t st,
+                         bool pdl) {
+  switch (b) {
+    case 1: return launch_chain_t<1>(cp, x_smem, stages, device, st, pdl);
+    case 2: return launch_chain_t<2>(cp, x_smem, stages, device, st, pdl);
+    case 3: return launch_chain_t<3>(cp, x_smem, stages, device, st, pdl);
+    case 4: return launch_chain_t<4>(cp, x_smem, stages, device, st, pdl);
+    case 5: return launch_chain_t<5>(cp, x_smem, stages, device, st, pdl);
+    case 6: return launch_chain_t<6>(cp, x_smem, stages, device, st, pdl);
+    case 7: return launch_chain_t<7>(cp, x_smem, stages, device, st, pdl);
+    case 8: return launch_chain_t<8>(cp, x_smem, stages, device, st, pdl);
+  }
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_gemv_mma(const GemvParams& p, int b, int device, cudaStream_t st, bool pdl) {
@@ -508,6 +577,7 @@ struct advspec_engine {
   float *dx = nullptr, *dx_save = nullptr, *dq = nullptr, *dlogits = nullptr;
   __nv_bfloat16 *dqkv = nullptr, *dattn = nullptr, *dh = nullptr;
   float *part_m = nullptr, *part_l = nullptr, *part_o = nullptr;
+  unsigned int* chain_bar = nullptr;  // grid-barrier words of gemv_chain_kernel
   AttnItem* items = nullptr;
   int items_cap = 0, n_items = 0, n_slots = 0;
   // fused tensor-core decode attention: work decomposition of the current batch
@@ -686,7 +756,7 @@ void free_all(advspec_engine* e) {
   if (e->graph) cudaGraphExecDestroy(e->graph);
   void* ptrs[] = {e->w, e->inv_freq, e->rope_cos, e->rope_sin, e->pkv, e->skv, e->p_tokens, e->p_x,
                   e->p_xn, e->p_qkv, e->p_attn, e->p_h, e->prefill_logits, e->dx, e->dx_save, e->dq,
-                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->items, e->s_pos, e->kv_maps,
+                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->chain_bar, e->items, e->s_pos, e->kv_maps,
                   e->s_slots, e->s_forced, e->s_seeds, e->s_suf_len, e->s_n_out, e->s_done,
                   e->s_cur_tok, e->s_out, e->samp_best, e->samp_idx};
   for (void* p : ptrs)
@@ -790,10 +860,45 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
     e->launches++;
     return r;
   };
+  // Chain mode: the four GEMVs between two attentions are phases of one persistent launch.
+  bool chain = g_chain && g_gemv_impl == 3 && !prof && e->attn_fused;
+  size_t chain_x_smem = 0;
+  int chain_stages = 0;
+  auto make_chain = [&](int l, ChainParams* cp) {
+    const LayerW w = layer_w(e, l);
+    const bool last = l + 1 == d.n_layers;
+    *cp = ChainParams{};
+    cp->ph[0] = ChainPhase{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, EPI_RESADD_F32, 0};
+    cp->ph[1] = ChainPhase{w.wgu, e->dx, w.mlp_norm, nullptr, e->dh, 2 * d.d_ff, dm, 1, EPI_GATED_BF16, 0};
+    cp->ph[2] = ChainPhase{w.wd, e->dh, nullptr, nullptr, e->dx, dm, d.d_ff, 0, EPI_RESADD_F32, 0};
+    if (last) {
+      cp->ph[3] = ChainPhase{lm_head_w(e), e->dx, final_norm_w(e), nullptr, e->dlogits, d.vocab_size, dm, 1, EPI_F32, 0};
+    } else {
+      const LayerW wn = layer_w(e, l + 1);
+      cp->ph[3] = ChainPhase{wn.wqkv, e->dx, wn.attn_norm, wn.bqkv, e->dqkv, QKV, dm, 1, EPI_BF16, 0};
+    }
+    cp->n_ph = 4;
+    cp->act = d.act;
+    cp->eps = d.norm_eps;
+    cp->bar = e->chain_bar;
+  };
+  if (chain) {
+    ChainParams cp;
+    make_chain(0, &cp);
+    chain = chain_plan(&cp, b, &chain_x_smem, &chain_stages);
+    if (chain && d.n_layers > 1) {
+      make_chain(d.n_layers - 1, &cp);
+      size_t xs2 = 0;
+      int st2 = 0;
+      chain = chain_plan(&cp, b, &xs2, &st2) && xs2 == chain_x_smem;
+    }
+  }
   for (int l = 0; l < d.n_layers; ++l) {
     const LayerW w = layer_w(e, l);
+    if (!chain || l == 0) {
     GemvParams g1{w.wqkv, e->dx, w.attn_norm, w.bqkv, e->dqkv, QKV, dm, 1, EPI_BF16, d.act, d.norm_eps};
     E_CUDA(e, gemv(g1));
+    }
     ADV_TRACE(e->stream, "gemv qkv");
     if (e->attn_fused) {
       AttnDecode2Params a2{};
@@ -860,6 +965,17 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
                            e->dattn, e->n_slots, d.head_dim));
       ADV_TRACE(e->stream, "attn_combine");
     }
+    if (chain) {
+      ChainParams cp;
+      make_chain(l, &cp);
+      size_t xs = 0;
+      int stg = 0;
+      chain_plan(&cp, b, &xs, &stg);
+      E_CUDA(e, launch_chain(cp, b, xs, stg, e->device, e->stream, true));
+      ADV_TRACE(e->stream, "gemv chain");
+      e->launches += 4;  // with the -1 above: attention + combine + chain = 3 launches per layer
+      continue;
+    }
     GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, EPI_RESADD_F32, d.act, d.norm_eps};
     E_CUDA(e, gemv(g2));
     ADV_TRACE(e->stream, "gemv o");
@@ -871,10 +987,12 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
     ADV_TRACE(e->stream, "gemv down");
     e->launches += 3;
   }
-  GemvParams gl{lm_head_w(e), e->dx, final_norm_w(e), nullptr, e->dlogits, d.vocab_size, dm, 1, EPI_F32,
-                d.act, d.norm_eps};
-  E_CUDA(e, gemv(gl));
-  ADV_TRACE(e->stream, "gemv lm_head");
+  if (!chain) {
+    GemvParams gl{lm_head_w(e), e->dx, final_norm_w(e), nullptr, e->dlogits, d.vocab_size, dm, 1, EPI_F32,
+                  d.act, d.norm_eps};
+    E_CUDA(e, gemv(gl));
+    ADV_TRACE(e->stream, "gemv lm_head");
+  }
   if (prof) {
     E_CUDA(e, cudaStreamSynchronize(e->stream));
     float total = 0.f;
@@ -1041,6 +1159,7 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   g_gemm_narrow = getenv("ADVSPEC_GEMM_NARROW") != nullptr;
   if (const char* tc = getenv("ADVSPEC_ATTN_PREFILL_TC")) g_attn_prefill_tc = atoi(tc) != 0;
   if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
+  if (const char* ch = getenv("ADVSPEC_CHAIN")) g_chain = atoi(ch) != 0;
 
   auto boot = [&]() -> advspec_status {
     const auto& d = e->d;
@@ -1091,6 +1210,8 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, dmalloc(&e->part_o, B * d.n_heads * (size_t)(max_splits + 1) * d.head_dim));
     e->items_cap = d.n_kv_heads * (((int)B * G + 3) / 4) * max_splits + (int)B * d.n_kv_heads * ((G + 3) / 4);
     E_CUDA(e, dmalloc(&e->items, (size_t)e->items_cap));
+    E_CUDA(e, dmalloc(&e->chain_bar, 4));
+    E_CUDA(e, cudaMemsetAsync(e->chain_bar, 0, 4 * sizeof(unsigned int), e->stream));
     E_CUDA(e, dmalloc(&e->s_pos, B));
     E_CUDA(e, cudaMemsetAsync(e->s_pos, 0, B * sizeof(int), e->stream));
     e->attn_fused = g_attn_impl == 2 && (d.head_dim == 64 || d.head_dim == 128) && G <= 16 && d.n_heads <= 255;

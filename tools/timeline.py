@@ -31,4 +31,6 @@ out = {"model": name, "b": b, "prompt": ptok, "decode_ms_per_step_events": tm.de
        "gemv_us_per_step": tl["gemv_us_per_step"], "gemv_gbs": gemv_bytes / (tl["gemv_us_per_step"] * 1e3),
        "step_gbs": step_bytes / (tl["us_per_step"] * 1e3)}
 out["attn_phases_ns"] = [ph[i + 1] - ph[i] for i in range(5)]
+if os.environ.get("TL_PHASES"):
+    out["phases_rel_ns"] = [int(ph[i]) - int(ph[0]) for i in range(16)]
 print(json.dumps(out, indent=1))
