@@ -279,6 +279,11 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
       : "memory");
 }
 // Sub-block barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads).
+// L2 prefetch hint for the 128-byte line holding gptr (fire and forget)
+__device__ __forceinline__ void prefetch_l2_line(const void* gptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -139,6 +139,17 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_chain_kernel(ChainParams p
     int tg = 0;
     for (int pi = 0; pi < p.n_ph; ++pi) {
       const ChainPhase& q = p.ph[pi];
+      constexpr int kMaxV = 4;
+      const bool in_regs = q.K <= kMaxV * kGmConsumers * 4;
+      float4 nw[kMaxV];  // RMSNorm weights: constants, fetched BEFORE the barrier (cold DRAM reads queue
+                         // behind the weight stream for ~2.4 us)
+      if (q.in_mode == 1 && in_regs) {
+#pragma unroll
+        for (int i = 0; i < kMaxV; ++i) {
+          const int k = (tid + i * kGmConsumers) * 4;
+          nw[i] = (k < q.K) ? *reinterpret_cast<const float4*>(q.norm_w + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       if (pi > 0) {
         chain_grid_barrier(p.bar, tid);
         phase_mark(1 + 3 * pi);
@@ -155,8 +166,6 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_chain_kernel(ChainParams p
       int xstride;
       if (q.in_mode == 1) {
         const float* xf = reinterpret_cast<const float*>(q.x);
-        constexpr int kMaxV = 4;
-        const bool in_regs = q.K <= kMaxV * kGmConsumers * 4;
         float4 xv[B][kMaxV];
         float ss[B];
 #pragma unroll
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_chain_kernel(ChainParams p
           for (int i = 0; i < kMaxV; ++i) {
             const int k = (tid + i * kGmConsumers) * 4;
             if (k < q.K) {
-              const float4 w4 = *reinterpret_cast<const float4*>(q.norm_w + k);
+              const float4 w4 = nw[i];
 #pragma unroll
               for (int b = 0; b < B; ++b) {
                 uint2 o;

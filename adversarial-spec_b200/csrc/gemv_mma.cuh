@@ -93,6 +93,24 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
     pdl_wait();
   } else {
     // ------------------------------ consumers -----------------------------
+    // Constants this kernel needs AFTER the dependency wait are fetched BEFORE it: a cold DRAM read
+    // issued behind a saturated weight stream waits ~2.4 us in the HBM queue (measured), and the
+    // RMSNorm weights (and the bias) are cold at every layer.
+    constexpr int kMaxV = 4;  // float4 per opponent per thread held in registers: K <= 4096
+    const bool in_regs = p.K <= kMaxV * kGmConsumers * 4;
+    float4 nw[kMaxV];
+    if (p.in_mode == 1) {
+      if (in_regs) {
+#pragma unroll
+        for (int i = 0; i < kMaxV; ++i) {
+          const int k = (tid + i * kGmConsumers) * 4;
+          nw[i] = (k < p.K) ? *reinterpret_cast<const float4*>(p.norm_w + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        for (int k = tid * 32; k < p.K; k += kGmConsumers * 32) prefetch_l2_line(p.norm_w + k);
+      }
+    }
+    if (p.bias != nullptr && tid * 32 < row_end - row_begin) prefetch_l2_line(p.bias + row_begin + tid * 32);
     pdl_wait();
     const uint8_t* xbase;  // bf16 rows of x, pitch xstride bytes
     int xstride;
@@ -100,8 +118,6 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
       // Fused RMSNorm of the fp32 residual stream.  When b*K is small (every model's d_model at b <= 4)
       // the row slice of each thread stays in registers between the sum of squares and the scaling.
       const float* xf = reinterpret_cast<const float*>(p.x);
-      constexpr int kMaxV = 4;  // float4 per opponent per thread held in registers: K <= 4096
-      const bool in_regs = p.K <= kMaxV * kGmConsumers * 4;
       float4 xv[B][kMaxV];
       float ss[B];
 #pragma unroll
@@ -146,7 +162,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
         for (int i = 0; i < kMaxV; ++i) {
           const int k = (tid + i * kGmConsumers) * 4;
           if (k < p.K) {
-            const float4 w4 = *reinterpret_cast<const float4*>(p.norm_w + k);
+            const float4 w4 = nw[i];
 #pragma unroll
             for (int b = 0; b < B; ++b) {
               uint2 o;
