@@ -123,13 +123,13 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   // Prefix tiles: one elected thread issues 2*NH TMA box copies per tile (K and V halves) that complete
   // on the stage's mbarrier.  Suffix tiles (a handful of tokens the CTA itself just extended): per-lane
   // cp.async into the same swizzled layout.
-  auto load_tile = [&](int tile) {
+  auto load_tile = [&](int tile, int issuer) {
     const int st = tile % NST;
     const int k0 = tb + tile * BN;
     __nv_bfloat16* dK = sKV + (size_t)st * 2 * TILE;
     __nv_bfloat16* dV = dK + TILE;
     if (is_prefix) {
-      if (tid == 0) {
+      if (tid == issuer) {
         mbar_arrive_expect_tx(&full_bar[st], 2u * TILE * 2u);
         const int row0 = hk * (int)p.pstride + k0;
 #pragma unroll
@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   // so this happens before the dependency wait)
   if (is_prefix) {
     for (int s = 0; s < NST; ++s) {
-      if (s < n_tiles) load_tile(s);
-      cp_async_commit();
+      if (s < n_tiles) load_tile(s, (s & 7) * 32);  // one warp per stage issues: the TMA ops of different
+      cp_async_commit();                             // stages enter the queue side by side, not one after another
     }
     phase_mark(1);
     pdl_wait();
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   __syncthreads();  // sQ complete; the appended k/v row is visible to this CTA's loads
   if (!is_prefix) {
     for (int s = 0; s < NST; ++s) {
-      if (s < n_tiles) load_tile(s);
+      if (s < n_tiles) load_tile(s, 0);
       cp_async_commit();
     }
   }
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     }
     if (jt + NST < n_tiles) {
       __syncthreads();  // stage jt % NST is free again
-      load_tile(jt + NST);
+      load_tile(jt + NST, 0);
     }
     cp_async_commit();
   }
@@ -318,26 +318,37 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < n_rows * DH; idx += 256) {
-    const int r = idx / DH, d = idx % DH;
+  // weights 2^(m_w - M) of the 8 warps' states, once per row (threads 0..127: warp w, row r)
+  float* s_c = s_o + 8 * 16 * OP;  // [8][16]
+  float* s_ML = s_c + 128;         // [16][2]: M, L of the merged row
+  if (tid < 16) {
     float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) M = fmaxf(M, s_m[w * 16 + r]);
-    float L = 0.f, O = 0.f;
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, s_m[w * 16 + tid]);
+    float L = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-      const float mw = s_m[w * 16 + r];
+      const float mw = s_m[w * 16 + tid];
       const float c = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
-      L += s_l[w * 16 + r] * c;
-      O += s_o[(w * 16 + r) * OP + d] * c;
+      s_c[w * 16 + tid] = c;
+      L += s_l[w * 16 + tid] * c;
     }
+    s_ML[2 * tid] = M;
+    s_ML[2 * tid + 1] = L;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n_rows * DH; idx += 256) {
+    const int r = idx / DH, d = idx % DH;
+    float O = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) O += s_o[(w * 16 + r) * OP + d] * s_c[w * 16 + r];
     const int gr = row_off + r;
     const int bi = o0 + gr / p.G, head = hk * p.G + gr % p.G;
     const int64_t ps = ((int64_t)bi * p.H + head) * p.n_slots + slot_out;
     p.part_o[ps * DH + d] = O;
     if (d == 0) {
-      p.part_m[ps] = M;
-      p.part_l[ps] = L;
+      p.part_m[ps] = s_ML[2 * r];
+      p.part_l[ps] = s_ML[2 * r + 1];
     }
   }
   phase_mark(5);
@@ -353,12 +364,20 @@ __global__ void __launch_bounds__(128) attn_decode_combine2_kernel(const float* 
                                                                    __nv_bfloat16* __restrict__ out,
                                                                    int n_slots, int DH) {
   __shared__ float w[320];
-  __shared__ float s_M, s_inv;
+  __shared__ float s_M;
   ktrace_mark(TK_COMBINE);
   if (!g_ktrace_on) pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x, tid = threadIdx.x;
   const int S = n_slots;
+  // the partial outputs do not depend on the weights: put the first 16 slots' loads of this thread's
+  // dimension in flight together with the m/l loads (one L2 round trip instead of two)
+  constexpr int PRE = 16;
+  float pre[PRE];
+  const bool own = tid < DH;
+  const float* po = part_o + (int64_t)row * S * DH + tid;
+#pragma unroll
+  for (int j = 0; j < PRE; ++j) pre[j] = (own && j < S) ? po[(int64_t)j * DH] : 0.f;
   float lv[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -389,26 +408,28 @@ __global__ void __launch_bounds__(128) attn_decode_combine2_kernel(const float* 
   part = warp_sum(part);
   if ((tid & 31) == 0) s_sum[tid >> 5] = part;
   __syncthreads();
-  if (tid == 0) {
-    const float L = s_sum[0] + s_sum[1] + s_sum[2] + s_sum[3];
-    s_inv = L > 0.f ? 1.0f / L : 0.f;
-  }
-  __syncthreads();
-  const float inv = s_inv;
+  const float L = s_sum[0] + s_sum[1] + s_sum[2] + s_sum[3];  // same fixed order in every thread
+  const float inv = L > 0.f ? 1.0f / L : 0.f;
   for (int d = tid; d < DH; d += 128) {
-    const float* po = part_o + (int64_t)row * S * DH + d;
+    const float* pd = part_o + (int64_t)row * S * DH + d;
     float a[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] = 0.f;
     int s = 0;
+    if (d == tid) {
+#pragma unroll
+      for (int j = 0; j < PRE; ++j)
+        if (j < S) a[j & 7] = fmaf(pre[j], w[j], a[j & 7]);
+      s = min(S, PRE);
+    }
     for (; s + 8 <= S; s += 8) {
       float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = po[(int64_t)(s + j) * DH];
+      for (int j = 0; j < 8; ++j) v[j] = pd[(int64_t)(s + j) * DH];
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] = fmaf(v[j], w[s + j], a[j]);
     }
-    for (; s < S; ++s) a[0] = fmaf(po[(int64_t)s * DH], w[s], a[0]);
+    for (; s < S; ++s) a[0] = fmaf(pd[(int64_t)s * DH], w[s], a[0]);
     const float tot = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     out[(int64_t)row * DH + d] = __float2bfloat16_rn(tot * inv);
   }

@@ -80,6 +80,7 @@ constexpr int kTraceCap = 8192;
 __device__ unsigned long long g_ktrace[kTraceCap];
 __device__ unsigned int g_ktrace_n = 0;
 __device__ int g_ktrace_on = 0;
+__device__ int g_l2_evict_first = 1;  // ADVSPEC_L2_EVICT_FIRST=0 turns the weight stream's L2 evict_first hint off (A/B)
 enum TraceKind : int { TK_GEMV = 1, TK_ATTN = 2, TK_SAMPLE = 3, TK_ROPE = 4, TK_COMBINE = 5, TK_SAMPLE_SCAN = 6 };
 __device__ __forceinline__ void ktrace_mark(int kind) {
   if (g_ktrace_on && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -188,6 +189,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 // ---------------------------------------------------------------------------
 // tcgen05 / TMEM — SASS: UTCHMMA, LDTM, UTCBAR
 // ---------------------------------------------------------------------------
@@ -278,7 +284,17 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
       : "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
-// Sub-block barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads).
+// Same copy with an L2 eviction policy (createpolicy): a 16 GB/step weight stream marked evict_first
+// leaves the small data every layer re-reads (activations, norm weights, tensor maps, RoPE rows,
+// attention partials) resident in the 126 MB L2 instead of flushing it once per layer.
+__device__ __forceinline__ void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                                  uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 // L2 prefetch hint for the 128-byte line holding gptr (fire and forget)
 __device__ __forceinline__ void prefetch_l2_line(const void* gptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr) : "memory");

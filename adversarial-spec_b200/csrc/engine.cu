@@ -161,12 +161,10 @@ cudaError_t set_smem(K kernel, int bytes) {
 template <int BN, int EPI>
 cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int device,
                           cudaStream_t st) {
-  static bool attr_done = false;
   auto kern = gemm_tc_kernel<BN, EPI>;
-  if (!attr_done) {
+  {  // function attributes are per device: set on every launch (host-side, microseconds)
     cudaError_t e = set_smem(kern, GemmCfg<BN>::kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + BN - 1) / BN);
   const int grid = std::min(tiles, num_sms(device));
@@ -285,11 +283,9 @@ cudaError_t launch_gemv_v1(const GemvParams& p, int b, int device, cudaStream_t 
 template <int B>
 cudaError_t launch_gemv_stream_t(const GemvParams& p, int device, cudaStream_t st, bool pdl) {
   constexpr int kMaxDyn = 220 * 1024;  // leaves room for the kernel's static shared memory
-  static bool attr_done = false;
-  if (!attr_done) {
+  {  // function attributes are per device: set on every launch (host-side, microseconds)
     cudaError_t e = set_smem(gemv_stream_kernel<B>, kMaxDyn);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   const size_t xbytes = (size_t)B * p.K * 2;
   // the normalised activations (in_mode 1) always live in shared memory; plain bf16 inputs are
@@ -318,11 +314,9 @@ size_t g_x_smem_max = 40000;  // ADVSPEC_X_SMEM_MAX: larger plain-bf16 inputs ar
 template <int B>
 cudaError_t launch_gemv_mma_t(const GemvParams& p, int device, cudaStream_t st, bool pdl) {
   constexpr int kMaxDyn = 232448 - 9 * 1024;  // 227 KB per CTA minus the kernel's 8.5 KB of static shared memory
-  static bool attr_done[64] = {};  // function attributes are per device
-  if (!attr_done[device & 63]) {
+  {  // function attributes are per device: set on every launch (host-side, microseconds)
     cudaError_t e = set_smem(gemv_mma_kernel<B>, kMaxDyn);
     if (e != cudaSuccess) return e;
-    attr_done[device & 63] = true;
   }
   const size_t xbytes = ((size_t)B * ((size_t)p.K * 2 + 16) + 127) / 128 * 128;
   int x_in_smem = 0;
@@ -368,11 +362,9 @@ bool chain_plan(ChainParams* cp, int b, size_t* x_smem_out, int* stages_out) {
 template <int B>
 cudaError_t launch_chain_t(const ChainParams& cp, size_t x_smem, int stages, int device, cudaStream_t st, bool pdl) {
   constexpr int kMaxDyn = 232448 - 9 * 1024;
-  static bool attr_done[64] = {};
-  if (!attr_done[device & 63]) {
+  {  // function attributes are per device: set on every launch (host-side, microseconds)
     cudaError_t e = set_smem(gemv_chain_kernel<B>, kMaxDyn);
     if (e != cudaSuccess) return e;
-    attr_done[device & 63] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(num_sms(device));  // one CTA per SM, all co-resident (the grid barrier needs it)
@@ -484,11 +476,9 @@ cudaError_t launch_attn_prefill_tc(const void* q, int64_t ldq, const void* kc, c
     if (err) *err = "cuTensorMapEncodeTiled failed (attention)";
     return cudaErrorInvalidValue;
   }
-  static bool done = false;
-  if (!done) {
+  {  // function attributes are per device: set on every launch (host-side, microseconds)
     cudaError_t e = set_smem(attn_prefill_tc_kernel, kAtSmem);
     if (e != cudaSuccess) return e;
-    done = true;
   }
   AttnPrefillTcParams p{reinterpret_cast<__nv_bfloat16*>(out), n_q, q_pos0, H, Hkv, (int)kv_stride,
                         1.0f / sqrtf(128.0f)};
@@ -514,22 +504,18 @@ cudaError_t launch_attn_decode2(const AttnDecode2Params& p, int n_ctas, int DH, 
   constexpr int NST = 6;
   dim3 g(n_ctas), blk(256);
   if (DH == 128) {
-    static bool done = false;
     const int smem = 16 * 128 * 2 + NST * 2 * 64 * 128 * 2 + 1024 + 128;  // + alignment slack + barriers
-    if (!done) {
+    {  // function attributes are per device: set on every launch (host-side, microseconds)
       cudaError_t e = set_smem(attn_decode_mma_kernel<128, NST>, smem);
       if (e != cudaSuccess) return e;
-      done = true;
     }
     return launch_pdl(attn_decode_mma_kernel<128, NST>, g, blk, smem, st, pdl, p);
   }
   if (DH == 64) {
-    static bool done = false;
     const int smem = 16 * 64 * 2 + NST * 2 * 64 * 64 * 2 + 1024 + 128;
-    if (!done) {
+    {  // function attributes are per device: set on every launch (host-side, microseconds)
       cudaError_t e = set_smem(attn_decode_mma_kernel<64, NST>, smem);
       if (e != cudaSuccess) return e;
-      done = true;
     }
     return launch_pdl(attn_decode_mma_kernel<64, NST>, g, blk, smem, st, pdl, p);
   }
@@ -1164,6 +1150,10 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   auto boot = [&]() -> advspec_status {
     const auto& d = e->d;
     E_CUDA(e, cudaSetDevice(device));
+    if (const char* ef = getenv("ADVSPEC_L2_EVICT_FIRST")) {
+      const int v = atoi(ef);
+      E_CUDA(e, cudaMemcpyToSymbol(g_l2_evict_first, &v, sizeof v));
+    }
     E_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     E_CUDA(e, cudaEventCreate(&e->ev0));
     E_CUDA(e, cudaEventCreate(&e->ev1));

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
                                               // start-to-start stamps are clean per-kernel costs
   if (warp == 8) {
     // ------------------------------ producer ------------------------------
+    const uint64_t pol = l2_policy_evict_first();
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % n_stages;
       const uint32_t ph = (uint32_t)(t / n_stages) & 1u;
@@ -86,9 +87,14 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
         mbar_arrive_expect_tx(&full_bar[s], cbytes * (uint32_t)rows);
       }
       __syncwarp();
-      if (lane < rows)  // rows <= RT
-        bulk_load_1d(ring + (size_t)s * kGmStageBytes + (size_t)lane * kGmRowPitch,
-                     p.W + (int64_t)(rb + lane) * p.K + kc, cbytes, &full_bar[s]);
+      if (lane < rows) {  // rows <= RT
+        if (g_l2_evict_first)
+          bulk_load_1d_hint(ring + (size_t)s * kGmStageBytes + (size_t)lane * kGmRowPitch,
+                            p.W + (int64_t)(rb + lane) * p.K + kc, cbytes, &full_bar[s], pol);
+        else
+          bulk_load_1d(ring + (size_t)s * kGmStageBytes + (size_t)lane * kGmRowPitch,
+                       p.W + (int64_t)(rb + lane) * p.K + kc, cbytes, &full_bar[s]);
+      }
     }
     pdl_wait();
   } else {
