@@ -348,7 +348,9 @@ __global__ void rope_decode_kernel(const __nv_bfloat16* __restrict__ qkv, float*
 struct SampleParams {
   const float* logits;       // [b][V], or [1][V] when broadcast_logits
   int broadcast_logits;      // first token: every opponent samples the prefill logits
-  int V;
+  int V;                     // vocabulary entries in `logits` (a tensor-parallel rank holds V_full / tp_size)
+  int v_off;                 // token id of logits[0] (tp_rank * V)
+  int n_ranks, rank_stride;  // merge: part_best/part_idx of rank r start r * rank_stride words further on
   float temperature;
   const int* slots;          // [b]
   const uint64_t* seeds;     // [max_seqs]
@@ -393,9 +395,10 @@ __global__ void __launch_bounds__(256) sample_partial_kernel(SampleParams p, flo
   float best = -INFINITY;
   int bidx = 0x7fffffff;
   for (int v = v0 + tid; v < v1; v += 256) {
+    const int tok = p.v_off + v;  // global token id: noise and tie rule do not depend on the sharding
     float sc = lg[v] * invT;
-    if (p.temperature > 0.f) sc -= logf(-logf(uniform01(seed, step, (uint32_t)v)));
-    if (sc > best || (sc == best && v < bidx)) { best = sc; bidx = v; }
+    if (p.temperature > 0.f) sc -= logf(-logf(uniform01(seed, step, (uint32_t)tok)));
+    if (sc > best || (sc == best && tok < bidx)) { best = sc; bidx = tok; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -437,9 +440,10 @@ __global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
     if (warp == 0) {
       float best = -INFINITY;
       int bidx = 0x7fffffff;
-      for (int c = lane; c < kSampleChunks; c += 32) {
-        const float ob = p.part_best[b * kSampleChunks + c];
-        const int oi = p.part_idx[b * kSampleChunks + c];
+      for (int c = lane; c < kSampleChunks * p.n_ranks; c += 32) {
+        const int r = c / kSampleChunks, cc = c % kSampleChunks;
+        const float ob = p.part_best[(int64_t)r * p.rank_stride + b * kSampleChunks + cc];
+        const int oi = p.part_idx[(int64_t)r * p.rank_stride + b * kSampleChunks + cc];
         if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
       }
 #pragma unroll

@@ -11,11 +11,18 @@
 //              split-KV attention (prefix shared, suffix private), combine,
 //              O GEMV(+res), norm+gate/up GEMV(+act*up), down GEMV(+res)]
 //              -> norm+lm_head GEMV -> Gumbel-max sample + next embedding
+// Tensor parallelism (one large opponent over tp_size GPUs, one process per GPU): a rank is the
+// same engine over a NARROWER model — its share of the query/KV heads, of the MLP columns and of
+// the vocabulary — plus three exchange points: an all-reduce of the residual stream after the
+// o-proj and after the down-proj (rank 0's partial carries the residual, so the sum IS the new
+// residual), and an all-gather of the per-rank sampler winners.  NCCL is bound at run time.
 // No CPU fallback exists: every compute entry point needs a CUDA device.
 #include "../../include/advspec_engine.h"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is dlopen'ed (advspec_tp_*)
 
 #include <algorithm>
 #include <cmath>
@@ -45,6 +52,50 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// NCCL bound at run time: a process that never asks for tensor parallelism never needs the library.
+struct NcclApi {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  std::string err;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+bool nccl_load(std::string* why) {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.lib) return true;
+  const char* env = getenv("ADVSPEC_NCCL_LIB");
+  const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    if (!n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) {
+    if (why) *why = std::string("cannot load NCCL (set ADVSPEC_NCCL_LIB): ") + (dlerror() ? dlerror() : "");
+    return false;
+  }
+  auto sym = [&](const char* n) { return dlsym(h, n); };
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(sym("ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(sym("ncclCommInitRank"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(sym("ncclCommDestroy"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(sym("ncclAllReduce"));
+  g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(sym("ncclAllGather"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce ||
+      !g_nccl.AllGather || !g_nccl.GetErrorString) {
+    if (why) *why = "the NCCL library lacks a required symbol";
+    return false;
+  }
+  g_nccl.lib = h;
+  return true;
+}
+
 constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v, size_t a = kAlign) { return (v + a - 1) / a * a; }
 
@@ -58,8 +109,24 @@ struct BlobLayout {
 
 inline int qkv_dim(const advspec_model_desc& d) { return (d.n_heads + 2 * d.n_kv_heads) * d.head_dim; }
 
+// The shape one tensor-parallel rank computes with: its share of the heads, of the MLP width and of
+// the vocabulary (lm_head rows); d_model, layers and the embedding table (v_full rows) are whole.
+struct LocalDesc {
+  advspec_model_desc d;
+  int v_full;
+};
+LocalDesc localize(const advspec_model_desc& full) {
+  LocalDesc r{full, full.vocab_size};
+  const int tp = full.tp_size > 1 ? full.tp_size : 1;
+  r.d.n_heads = full.n_heads / tp;
+  r.d.n_kv_heads = full.n_kv_heads / tp;
+  r.d.d_ff = full.d_ff / tp;
+  r.d.vocab_size = full.vocab_size / tp;
+  return r;
+}
+
 // Order and alignment restated in adversarial-spec_b200/weights.py (checked by tests).
-BlobLayout make_layout(const advspec_model_desc& d) {
+BlobLayout make_layout(const advspec_model_desc& d, int v_full) {
   BlobLayout L;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -68,7 +135,7 @@ BlobLayout make_layout(const advspec_model_desc& d) {
     return o;
   };
   const size_t dm = d.d_model, qkv = qkv_dim(d), hd = (size_t)d.n_heads * d.head_dim;
-  L.embed = take((size_t)d.vocab_size * dm * 2);
+  L.embed = take((size_t)v_full * dm * 2);
   L.layers.resize(d.n_layers);
   for (int l = 0; l < d.n_layers; ++l) {
     auto& o = L.layers[l];
@@ -103,7 +170,16 @@ bool desc_ok(const advspec_model_desc* d, std::string* why) {
     return bad("d_model, d_ff and n_heads*head_dim must be multiples of 8");
   if (d->max_seqs < 1 || d->max_seqs > 8) return bad("max_seqs must be in 1..8");
   if (d->max_prefix_tokens < 1 || d->max_new_tokens < 1) return bad("bad KV capacities");
-  if (d->tp_rank != 0 || d->tp_size != 1) return bad("tensor parallelism is reserved (tp_size must be 1)");
+  if (d->tp_size != 1) {
+    const int tp = d->tp_size;
+    if (tp != 2 && tp != 4 && tp != 8) return bad("tp_size must be 1, 2, 4 or 8");
+    if (d->tp_rank < 0 || d->tp_rank >= tp) return bad("tp_rank outside 0..tp_size-1");
+    if (d->n_heads % tp || d->n_kv_heads % tp) return bad("tp_size must divide n_heads and n_kv_heads");
+    if (d->d_ff % (8 * tp) || d->vocab_size % tp) return bad("tp_size must divide d_ff/8 and vocab_size");
+    if (d->tied_lm_head) return bad("tensor parallelism with a tied lm_head is not supported");
+  } else if (d->tp_rank != 0) {
+    return bad("tp_rank must be 0 when tp_size is 1");
+  }
   if (d->act != 0 && d->act != 1) return bad("act must be 0 (SiLU) or 1 (tanh GELU)");
   return true;
 }
@@ -578,8 +654,16 @@ struct advspec_engine {
   uint64_t* s_seeds = nullptr;
   int *s_suf_len = nullptr, *s_n_out = nullptr, *s_done = nullptr, *s_cur_tok = nullptr,
       *s_out = nullptr;
-  float* samp_best = nullptr;  // [max_seqs][kSampleChunks] partial winners of the sampler
-  int* samp_idx = nullptr;
+  // partial winners of the sampler: [tp_size][2][max_seqs * kSampleChunks] 4-byte words (scores, then
+  // token ids); a rank fills its own slice, tensor-parallel ranks all-gather the rest
+  float* samp_best = nullptr;
+  int* samp_idx = nullptr;  // = samp_best + max_seqs * kSampleChunks (this rank's slice)
+  uint32_t* samp_pack = nullptr;
+
+  // tensor parallelism
+  int V_full = 0;  // rows of the embedding table / range of token ids (d.vocab_size is this rank's share)
+  int tp_rank = 0, tp_size = 1;
+  ncclComm_t comm = nullptr;
 
   // host-side bookkeeping
   int prefix_gen = 0;     // id of the live prefix (0 = none)
@@ -672,6 +756,28 @@ const __nv_bfloat16* lm_head_w(advspec_engine* e) {
 }
 const float* final_norm_w(advspec_engine* e) { return reinterpret_cast<const float*>(e->wp(e->lay.final_norm)); }
 
+// Tensor-parallel exchange: sum the ranks' partial residual streams in place (rank 0's partial
+// already carries the residual, so the sum is the new residual on every rank).
+advspec_status tp_allreduce(advspec_engine* e, float* buf, size_t count) {
+  if (e->tp_size == 1) return ADVSPEC_OK;
+  if (!e->comm) {
+    e->fail("tensor-parallel engine used before advspec_tp_init");
+    return ADVSPEC_ERR_STATE;
+  }
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, count, ncclFloat32, ncclSum, e->comm, e->stream);
+  if (r != ncclSuccess) {
+    e->fail("ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+    return ADVSPEC_ERR_CUDA;
+  }
+  e->launches++;
+  return ADVSPEC_OK;
+}
+// Epilogue of a row-split product (o-proj, down-proj): rank 0 adds into the residual, the other
+// ranks overwrite their copy with the bare partial; tp_allreduce follows.
+inline int tp_resadd_epi(const advspec_engine* e) {
+  return (e->tp_size > 1 && e->tp_rank != 0) ? EPI_F32 : EPI_RESADD_F32;
+}
+
 // One GEMM of the prefill path (tcgen05 unless the test-only debug flag asks for the check kernel).
 advspec_status prefill_gemm(advspec_engine* e, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B,
                             int64_t ldb, void* C, int64_t ldc, const float* bias, int M, int N, int K,
@@ -724,13 +830,17 @@ advspec_status prefill_chunk(advspec_engine* e, int m, int pos0) {
     } else {
       E_CUDA(e, launch_attn_prefill(ap, d.head_dim, (e->debug_flags & 2) ? 1 : 0, e->stream, nullptr));
     }
-    s = prefill_gemm(e, e->p_attn, HD, w.wo, HD, e->p_x, dm, nullptr, m, dm, HD, EPI_RESADD_F32);
+    s = prefill_gemm(e, e->p_attn, HD, w.wo, HD, e->p_x, dm, nullptr, m, dm, HD, tp_resadd_epi(e));
+    if (s) return s;
+    s = tp_allreduce(e, e->p_x, (size_t)m * dm);
     if (s) return s;
     rmsnorm_kernel<<<m, 256, 0, e->stream>>>(e->p_x, w.mlp_norm, e->p_xn, dm, d.norm_eps);
     E_CUDA(e, cudaGetLastError());
     s = prefill_gemm(e, e->p_xn, dm, w.wgu, dm, e->p_h, d.d_ff, nullptr, m, 2 * d.d_ff, dm, EPI_GATED_BF16);
     if (s) return s;
-    s = prefill_gemm(e, e->p_h, d.d_ff, w.wd, d.d_ff, e->p_x, dm, nullptr, m, dm, d.d_ff, EPI_RESADD_F32);
+    s = prefill_gemm(e, e->p_h, d.d_ff, w.wd, d.d_ff, e->p_x, dm, nullptr, m, dm, d.d_ff, tp_resadd_epi(e));
+    if (s) return s;
+    s = tp_allreduce(e, e->p_x, (size_t)m * dm);
     if (s) return s;
     e->launches += 4;
   }
@@ -740,11 +850,13 @@ advspec_status prefill_chunk(advspec_engine* e, int m, int pos0) {
 void free_all(advspec_engine* e) {
   cudaSetDevice(e->device);
   if (e->graph) cudaGraphExecDestroy(e->graph);
+  if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  e->comm = nullptr;
   void* ptrs[] = {e->w, e->inv_freq, e->rope_cos, e->rope_sin, e->pkv, e->skv, e->p_tokens, e->p_x,
                   e->p_xn, e->p_qkv, e->p_attn, e->p_h, e->prefill_logits, e->dx, e->dx_save, e->dq,
                   e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->chain_bar, e->items, e->s_pos, e->kv_maps,
                   e->s_slots, e->s_forced, e->s_seeds, e->s_suf_len, e->s_n_out, e->s_done,
-                  e->s_cur_tok, e->s_out, e->samp_best, e->samp_idx};
+                  e->s_cur_tok, e->s_out, e->samp_pack};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -847,7 +959,7 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
     return r;
   };
   // Chain mode: the four GEMVs between two attentions are phases of one persistent launch.
-  bool chain = g_chain && g_gemv_impl == 3 && !prof && e->attn_fused;
+  bool chain = g_chain && g_gemv_impl == 3 && !prof && e->attn_fused && e->tp_size == 1;
   size_t chain_x_smem = 0;
   int chain_stages = 0;
   auto make_chain = [&](int l, ChainParams* cp) {
@@ -962,14 +1074,16 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       e->launches += 4;  // with the -1 above: attention + combine + chain = 3 launches per layer
       continue;
     }
-    GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, EPI_RESADD_F32, d.act, d.norm_eps};
+    GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, tp_resadd_epi(e), d.act, d.norm_eps};
     E_CUDA(e, gemv(g2));
     ADV_TRACE(e->stream, "gemv o");
+    if (advspec_status ts = tp_allreduce(e, e->dx, (size_t)b * dm)) return ts;
     GemvParams g3{w.wgu, e->dx, w.mlp_norm, nullptr, e->dh, 2 * d.d_ff, dm, 1, EPI_GATED_BF16, d.act, d.norm_eps};
     E_CUDA(e, gemv(g3));
     ADV_TRACE(e->stream, "gemv gate_up");
-    GemvParams g4{w.wd, e->dh, nullptr, nullptr, e->dx, dm, d.d_ff, 0, EPI_RESADD_F32, d.act, d.norm_eps};
+    GemvParams g4{w.wd, e->dh, nullptr, nullptr, e->dx, dm, d.d_ff, 0, tp_resadd_epi(e), d.act, d.norm_eps};
     E_CUDA(e, gemv(g4));
+    if (advspec_status ts = tp_allreduce(e, e->dx, (size_t)b * dm)) return ts;
     ADV_TRACE(e->stream, "gemv down");
     e->launches += 3;
   }
@@ -1001,6 +1115,9 @@ SampleParams make_sample_params(advspec_engine* e, float temperature, int eos_id
   sp.logits = broadcast ? e->prefill_logits : e->dlogits;
   sp.broadcast_logits = broadcast ? 1 : 0;
   sp.V = e->d.vocab_size;
+  sp.v_off = e->tp_rank * e->d.vocab_size;
+  sp.n_ranks = e->tp_size;
+  sp.rank_stride = 2 * e->d.max_seqs * kSampleChunks;
   sp.temperature = temperature;
   sp.slots = e->s_slots;
   sp.seeds = e->s_seeds;
@@ -1014,8 +1131,8 @@ SampleParams make_sample_params(advspec_engine* e, float temperature, int eos_id
   sp.forced = forced;
   sp.pos_b = e->s_pos;
   sp.prefix_len = e->prefix_len;
-  sp.part_best = forced ? nullptr : e->samp_best;
-  sp.part_idx = forced ? nullptr : e->samp_idx;
+  sp.part_best = forced ? nullptr : reinterpret_cast<const float*>(e->samp_pack);
+  sp.part_idx = forced ? nullptr : reinterpret_cast<const int*>(e->samp_pack) + e->d.max_seqs * kSampleChunks;
   sp.cur_tok = e->s_cur_tok;
   sp.embed = embed_w(e);
   sp.x = e->dx;
@@ -1033,6 +1150,15 @@ cudaError_t launch_sampler(advspec_engine* e, const SampleParams& sp, int n, boo
     if (r != cudaSuccess) return r;
     e->launches++;
     pdl = true;
+    if (e->tp_size > 1) {
+      // every rank scanned its share of the vocabulary: gather the winners, then all merge identically
+      if (!e->comm) return cudaErrorNotReady;
+      const size_t words = (size_t)sp.rank_stride;
+      ncclResult_t nr = g_nccl.AllGather(e->samp_pack + (size_t)e->tp_rank * words, e->samp_pack, words, ncclUint32,
+                                         e->comm, e->stream);
+      if (nr != ncclSuccess) return cudaErrorUnknown;
+      e->launches++;
+    }
   }
   e->launches++;
   return launch_pdl(sample_kernel, dim3(n), dim3(1024), 0, e->stream, pdl, sp);
@@ -1083,12 +1209,14 @@ extern "C" {
 
 size_t advspec_weight_blob_bytes(const advspec_model_desc* desc) {
   if (!desc_ok(desc, nullptr)) return 0;
-  return make_layout(*desc).total;
+  const LocalDesc ld = localize(*desc);
+  return make_layout(ld.d, ld.v_full).total;
 }
 
 size_t advspec_weight_offset(const advspec_model_desc* desc, int32_t layer, const char* name) {
   if (!desc_ok(desc, nullptr) || !name) return (size_t)-1;
-  const BlobLayout L = make_layout(*desc);
+  const LocalDesc ld = localize(*desc);
+  const BlobLayout L = make_layout(ld.d, ld.v_full);
   const std::string n(name);
   if (layer < 0) {
     if (n == "embed") return L.embed;
@@ -1131,9 +1259,13 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     return ADVSPEC_ERR_CUDA;
   }
   advspec_engine* e = new advspec_engine();
-  e->d = *desc;
+  const LocalDesc ld = localize(*desc);
+  e->d = ld.d;  // from here on every shape is this rank's share
+  e->V_full = ld.v_full;
+  e->tp_rank = desc->tp_size > 1 ? desc->tp_rank : 0;
+  e->tp_size = desc->tp_size > 1 ? desc->tp_size : 1;
   e->device = device;
-  e->lay = make_layout(*desc);
+  e->lay = make_layout(ld.d, ld.v_full);
   const char* dbg = getenv("ADVSPEC_DEBUG_FLAGS");
   e->debug_flags = dbg ? atoi(dbg) : 0;
   e->use_graph = getenv("ADVSPEC_NO_GRAPH") == nullptr;
@@ -1228,8 +1360,12 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, dmalloc(&e->s_done, B));
     E_CUDA(e, dmalloc(&e->s_cur_tok, B));
     E_CUDA(e, dmalloc(&e->s_out, B * (size_t)d.max_new_tokens));
-    E_CUDA(e, dmalloc(&e->samp_best, B * (size_t)kSampleChunks));
-    E_CUDA(e, dmalloc(&e->samp_idx, B * (size_t)kSampleChunks));
+    {
+      const size_t b64 = B * (size_t)kSampleChunks;
+      E_CUDA(e, dmalloc(&e->samp_pack, (size_t)e->tp_size * 2 * b64));
+      e->samp_best = reinterpret_cast<float*>(e->samp_pack + (size_t)e->tp_rank * 2 * b64);
+      e->samp_idx = reinterpret_cast<int*>(e->samp_best + b64);
+    }
     E_CUDA(e, cudaMemsetAsync(e->s_suf_len, 0, B * sizeof(int), e->stream));
     E_CUDA(e, cudaMemsetAsync(e->s_n_out, 0, B * sizeof(int), e->stream));
     E_CUDA(e, cudaMemsetAsync(e->s_done, 0, B * sizeof(int), e->stream));
@@ -1267,6 +1403,62 @@ void advspec_engine_destroy(advspec_engine* e) {
   delete e;
 }
 
+advspec_status advspec_tp_unique_id(uint8_t* out128) {
+  if (!out128) return ADVSPEC_ERR_INVALID;
+  std::string why;
+  if (!nccl_load(&why)) {
+    g_create_error = why;
+    return ADVSPEC_ERR_STATE;
+  }
+  static_assert(sizeof(ncclUniqueId) == 128, "the ABI carries the NCCL unique id as 128 opaque bytes");
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) {
+    g_create_error = std::string("ncclGetUniqueId failed: ") + g_nccl.GetErrorString(r);
+    return ADVSPEC_ERR_CUDA;
+  }
+  memcpy(out128, &id, 128);
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_tp_init(advspec_engine* e, const uint8_t* id128) {
+  if (!e || !id128) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->tp_size == 1) return ADVSPEC_OK;  // nothing to join
+  if (e->comm) {
+    e->fail("advspec_tp_init called twice on one handle");
+    return ADVSPEC_ERR_STATE;
+  }
+  std::string why;
+  if (!nccl_load(&why)) {
+    e->fail("%s", why.c_str());
+    return ADVSPEC_ERR_STATE;
+  }
+  E_CUDA(e, cudaSetDevice(e->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&e->comm, e->tp_size, id, e->tp_rank);  // blocks until all ranks join
+  if (r != ncclSuccess) {
+    e->comm = nullptr;
+    e->fail("ncclCommInitRank(rank %d of %d) failed: %s", e->tp_rank, e->tp_size, g_nccl.GetErrorString(r));
+    return ADVSPEC_ERR_CUDA;
+  }
+  // one eager round of both collectives: NCCL's lazy setup (buffers, channels) must not happen for the
+  // first time inside the decode step's stream capture
+  const size_t words = (size_t)2 * e->d.max_seqs * kSampleChunks;
+  E_CUDA(e, cudaMemsetAsync(e->dx, 0, (size_t)e->d.max_seqs * e->d.d_model * sizeof(float), e->stream));
+  ncclResult_t r1 = g_nccl.AllReduce(e->dx, e->dx, (size_t)e->d.max_seqs * e->d.d_model, ncclFloat32, ncclSum,
+                                     e->comm, e->stream);
+  ncclResult_t r2 = g_nccl.AllGather(e->samp_pack + (size_t)e->tp_rank * words, e->samp_pack, words, ncclUint32,
+                                     e->comm, e->stream);
+  if (r1 != ncclSuccess || r2 != ncclSuccess) {
+    e->fail("NCCL warm-up collectives failed: %s", g_nccl.GetErrorString(r1 != ncclSuccess ? r1 : r2));
+    return ADVSPEC_ERR_CUDA;
+  }
+  E_CUDA(e, cudaStreamSynchronize(e->stream));
+  return ADVSPEC_OK;
+}
+
 advspec_status advspec_load_weights(advspec_engine* e, const void* host_blob, size_t bytes) {
   if (!e) return ADVSPEC_ERR_INVALID;
   std::lock_guard<std::mutex> lk(e->mu);
@@ -1294,10 +1486,11 @@ advspec_status advspec_init_weights_random(advspec_engine* e, uint64_t seed, flo
     fill_f32_kernel<<<64, 256, 0, e->stream>>>(reinterpret_cast<float*>(e->w + off), (int64_t)n, v);
   };
   const size_t dm = d.d_model, QKV = qkv_dim(d), HD = (size_t)d.n_heads * d.head_dim;
-  rnd(e->lay.embed, (size_t)d.vocab_size * dm, 1);
+  rnd(e->lay.embed, (size_t)e->V_full * dm, 1);  // replicated: the same table on every tensor-parallel rank
+  const uint64_t rk = (uint64_t)e->tp_rank << 40;  // sharded tensors: an independent draw per rank
   for (int l = 0; l < d.n_layers; ++l) {
     const auto& o = e->lay.layers[l];
-    const uint64_t t = 16 * (uint64_t)(l + 1);
+    const uint64_t t = (16 * (uint64_t)(l + 1)) ^ rk;
     ones(o.attn_norm, dm, 1.0f);
     rnd(o.wqkv, QKV * dm, t + 1);
     if (d.qkv_bias) ones(o.bqkv, QKV, 0.0f);
@@ -1307,7 +1500,7 @@ advspec_status advspec_init_weights_random(advspec_engine* e, uint64_t seed, flo
     rnd(o.wd, dm * (size_t)d.d_ff, t + 4);
   }
   ones(e->lay.final_norm, dm, 1.0f);
-  if (!d.tied_lm_head) rnd(e->lay.lm_head, (size_t)d.vocab_size * dm, 2);
+  if (!d.tied_lm_head) rnd(e->lay.lm_head, (size_t)d.vocab_size * dm, 2 ^ rk);
   E_CUDA(e, cudaGetLastError());
   E_CUDA(e, cudaStreamSynchronize(e->stream));
   e->weights_ready = true;
@@ -1343,7 +1536,7 @@ static advspec_status prefill_impl(advspec_engine* e, const int32_t* tokens, int
     return ADVSPEC_ERR_INVALID;
   }
   for (int i = 0; i < n; ++i)
-    if (tokens[i] < 0 || tokens[i] >= d.vocab_size) {
+    if (tokens[i] < 0 || tokens[i] >= e->V_full) {
       e->fail("token %d at position %d outside the vocabulary", tokens[i], i);
       return ADVSPEC_ERR_INVALID;
     }
@@ -1607,7 +1800,7 @@ advspec_status advspec_decode_step(advspec_engine* e, const int32_t* seq_ids, in
   advspec_status st = setup_batch(e, seq_ids, n, &slots);
   if (st != ADVSPEC_OK) return st;
   for (int i = 0; i < n; ++i) {
-    if (forced_tokens[i] < 0 || forced_tokens[i] >= d.vocab_size) {
+    if (forced_tokens[i] < 0 || forced_tokens[i] >= e->V_full) {
       e->fail("forced token %d outside the vocabulary", forced_tokens[i]);
       return ADVSPEC_ERR_INVALID;
     }

@@ -73,7 +73,8 @@ class Timing(C.Structure):
 
 EXPORTED_SYMBOLS = [
     "advspec_weight_blob_bytes", "advspec_weight_offset", "advspec_engine_create",
-    "advspec_engine_destroy", "advspec_last_error", "advspec_load_weights",
+    "advspec_engine_destroy", "advspec_last_error", "advspec_tp_unique_id", "advspec_tp_init",
+    "advspec_load_weights",
     "advspec_init_weights_random", "advspec_set_rope_inv_freq", "advspec_prefill", "advspec_fork",
     "advspec_decode", "advspec_decode_step", "advspec_get_logits", "advspec_prefill_logits",
     "advspec_release_seqs", "advspec_release_prefix", "advspec_prefix_kv_region",
@@ -103,6 +104,8 @@ def load_library() -> C.CDLL:
         "advspec_engine_create": (i32, [P(ModelDesc), i32, P(vp)]),
         "advspec_engine_destroy": (None, [vp]),
         "advspec_last_error": (C.c_char_p, [vp]),
+        "advspec_tp_unique_id": (i32, [P(C.c_uint8)]),
+        "advspec_tp_init": (i32, [vp, P(C.c_uint8)]),
         "advspec_load_weights": (i32, [vp, vp, sz]),
         "advspec_init_weights_random": (i32, [vp, C.c_uint64, f32]),
         "advspec_set_rope_inv_freq": (i32, [vp, P(f32), i32]),
@@ -135,14 +138,16 @@ def load_library() -> C.CDLL:
     return lib
 
 
-def make_desc(spec: ModelSpec, max_prefix_tokens: int, max_new_tokens: int, max_seqs: int) -> ModelDesc:
+def make_desc(spec: ModelSpec, max_prefix_tokens: int, max_new_tokens: int, max_seqs: int,
+              tp_rank: int = 0, tp_size: int = 1) -> ModelDesc:
+    """`spec` is always the WHOLE model; tp_rank/tp_size select the share one handle holds."""
     d = ModelDesc()
     d.abi_version = ABI_VERSION
     d.n_layers, d.d_model, d.n_heads, d.n_kv_heads = spec.n_layers, spec.d_model, spec.n_heads, spec.n_kv_heads
     d.head_dim, d.d_ff, d.vocab_size = spec.head_dim, spec.d_ff, spec.vocab_size
     d.act, d.qkv_bias, d.tied_lm_head = spec.act, int(spec.qkv_bias), int(spec.tied_lm_head)
     d.max_prefix_tokens, d.max_new_tokens, d.max_seqs = max_prefix_tokens, max_new_tokens, max_seqs
-    d.tp_rank, d.tp_size = 0, 1
+    d.tp_rank, d.tp_size = tp_rank, tp_size
     d.rope_theta, d.norm_eps, d.embed_scale = spec.rope_theta, spec.norm_eps, spec.embed_scale
     return d
 
@@ -166,11 +171,13 @@ class Engine:
     ctypes releases the GIL for the duration of each call)."""
 
     def __init__(self, spec: ModelSpec, device: int = 0, max_prefix_tokens: int = 4096 + 1024,
-                 max_new_tokens: int = 1024, max_seqs: int = 8):
+                 max_new_tokens: int = 1024, max_seqs: int = 8, tp_rank: int = 0, tp_size: int = 1):
         self.lib = load_library()
         self.spec = spec
         self.device = device
-        self.desc = make_desc(spec, max_prefix_tokens, max_new_tokens, max_seqs)
+        self.tp_rank, self.tp_size = tp_rank, tp_size
+        self.vocab_local = spec.vocab_size // tp_size  # columns of this handle's logits
+        self.desc = make_desc(spec, max_prefix_tokens, max_new_tokens, max_seqs, tp_rank, tp_size)
         h = C.c_void_p()
         st = self.lib.advspec_engine_create(C.byref(self.desc), device, C.byref(h))
         if st != 0:
@@ -192,6 +199,23 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    # -- tensor parallelism (one process per GPU; see include/advspec_engine.h) ----------
+    @staticmethod
+    def tp_unique_id() -> bytes:
+        lib = load_library()
+        buf = (C.c_uint8 * 128)()
+        st = lib.advspec_tp_unique_id(buf)
+        if st != 0:
+            raise EngineError(st, (lib.advspec_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def tp_init(self, unique_id: bytes) -> None:
+        """Join this handle's NCCL communicator; every rank calls it, concurrently."""
+        if len(unique_id) != 128:
+            raise ValueError("the NCCL unique id is 128 bytes")
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.advspec_tp_init(self.h, buf))
 
     # -- weights -----------------------------------------------------------
     def load_weights(self, blob: np.ndarray) -> None:
@@ -233,13 +257,13 @@ class Engine:
         self._check(self.lib.advspec_decode_step(self.h, _p(ids, C.c_int32), len(ids), _p(f, C.c_int32)))
 
     def get_logits(self, n: int = 1) -> np.ndarray:
-        out = np.zeros((n, self.spec.vocab_size), dtype=np.float32)
+        out = np.zeros((n, self.vocab_local), dtype=np.float32)
         self._check(self.lib.advspec_get_logits(self.h, n, _p(out, C.c_float)))
         return out
 
     def prefill_logits(self, tokens: Sequence[int]) -> np.ndarray:
         t = _i32(tokens)
-        out = np.zeros((t.size, self.spec.vocab_size), dtype=np.float32)
+        out = np.zeros((t.size, self.vocab_local), dtype=np.float32)
         self._check(self.lib.advspec_prefill_logits(self.h, _p(t, C.c_int32), t.size, _p(out, C.c_float)))
         return out
 

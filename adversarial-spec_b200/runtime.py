@@ -11,6 +11,9 @@ Knobs come from the environment so the reference's CLI surface stays unchanged
   ADVSPEC_WEIGHTS_DIR     directory of <model>.blob files; absent -> seeded random init on device
   ADVSPEC_DEVICES         comma list of CUDA devices to use (default: the current/only one)
   ADVSPEC_PLACEMENT       "batch" (default: same-weight opponents share a GPU) | "spread"
+  ADVSPEC_TP              tensor-parallel width for every local model: the process must run under
+                          torchrun with WORLD_SIZE == ADVSPEC_TP, all ranks make the same calls
+                          (one large opponent over 8 GPUs)
 """
 
 from __future__ import annotations
@@ -44,6 +47,37 @@ def visible_devices() -> list[int]:
     if "LOCAL_RANK" in os.environ and _env_int("WORLD_SIZE", 1) > 1:
         return [_env_int("LOCAL_RANK", 0)]  # one process per GPU under torchrun
     return [0]
+
+
+def tp_world() -> tuple[int, int]:
+    """(rank, size) of the tensor-parallel group this process belongs to; (0, 1) when ADVSPEC_TP is unset."""
+    tp = _env_int("ADVSPEC_TP", 1)
+    if tp <= 1:
+        return 0, 1
+    world = _env_int("WORLD_SIZE", 1)
+    if world != tp:
+        raise RuntimeError(f"ADVSPEC_TP={tp} needs torchrun with WORLD_SIZE={tp} (got {world}): one process per GPU")
+    return _env_int("RANK", 0), tp
+
+
+def create_tp_engine(spec: ModelSpec, device: int, max_prefix_tokens: int, max_new_tokens: int, max_seqs: int,
+                     tp_rank: int, tp_size: int) -> eng.Engine:
+    """This rank's handle of a tensor-parallel engine: rank 0 draws the NCCL id, torch.distributed
+    (the plumbing; any backend) carries it to the others, every rank joins (include/advspec_engine.h)."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        dist.init_process_group("gloo")  # 128 bytes of plumbing; the engine owns its NCCL communicator
+    e = eng.Engine(spec, device, max_prefix_tokens, max_new_tokens, max_seqs, tp_rank=tp_rank, tp_size=tp_size)
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if tp_rank == 0:
+        buf = torch.frombuffer(bytearray(eng.Engine.tp_unique_id()), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        buf = buf.cuda(device)
+    dist.broadcast(buf, src=0)
+    e.tp_init(bytes(buf.cpu().numpy().tobytes()))
+    return e
 
 
 @dataclass
@@ -83,11 +117,16 @@ class EnginePool:
                 cap_prefix = max(need_prefix, _env_int("ADVSPEC_MIN_PREFIX", 0))
                 cap_prefix = (cap_prefix + 255) // 256 * 256
                 cap_new = max(need_new, 16)
-                e = eng.Engine(spec, device, cap_prefix, cap_new, MAX_BATCH)
+                tp_rank, tp_size = tp_world()
+                if tp_size > 1:
+                    e = create_tp_engine(spec, device, cap_prefix, cap_new, MAX_BATCH, tp_rank, tp_size)
+                else:
+                    e = eng.Engine(spec, device, cap_prefix, cap_new, MAX_BATCH)
                 wdir = os.environ.get("ADVSPEC_WEIGHTS_DIR")
                 blob_path = os.path.join(wdir, f"{spec.name}.blob") if wdir else None
                 if blob_path and os.path.exists(blob_path):
-                    e.load_weights(np.fromfile(blob_path, dtype=np.uint8))
+                    from .weights import shard_blob
+                    e.load_weights(shard_blob(np.fromfile(blob_path, dtype=np.uint8), spec, tp_rank, tp_size))
                 else:
                     e.init_weights_random(_env_int("ADVSPEC_WEIGHT_SEED", 0), 0.02)
                 r = _Resident(e, SyntheticTokenizer(spec.vocab_size), max_prefix=cap_prefix, max_new=cap_new)

@@ -16,7 +16,7 @@ is exact.
 
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, replace
 
 import numpy as np
 
@@ -35,7 +35,21 @@ class BlobLayout:
     total: int
 
 
-def blob_layout(spec: ModelSpec) -> BlobLayout:
+def tp_local_spec(spec: ModelSpec, tp_size: int) -> ModelSpec:
+    """The shape ONE tensor-parallel rank computes with (restates `localize` in csrc/engine.cu):
+    its share of the heads, of the MLP width and of the lm_head rows; d_model and depth are whole."""
+    if tp_size == 1:
+        return spec
+    if spec.n_heads % tp_size or spec.n_kv_heads % tp_size or spec.d_ff % (8 * tp_size) \
+            or spec.vocab_size % tp_size or spec.tied_lm_head:
+        raise ValueError(f"{spec.name} cannot be split {tp_size} ways")
+    return replace(spec, n_heads=spec.n_heads // tp_size, n_kv_heads=spec.n_kv_heads // tp_size,
+                   d_ff=spec.d_ff // tp_size, vocab_size=spec.vocab_size // tp_size)
+
+
+def blob_layout(spec: ModelSpec, embed_rows: int | None = None) -> BlobLayout:
+    """`embed_rows`: rows of the embedding table when `spec` is a tensor-parallel share (the table
+    is replicated whole on every rank)."""
     off = 0
     offsets: dict = {}
 
@@ -46,7 +60,7 @@ def blob_layout(spec: ModelSpec) -> BlobLayout:
         off = _align(off + n)
 
     d, qkv, hd = spec.d_model, spec.qkv_dim, spec.n_heads * spec.head_dim
-    take((-1, "embed"), (spec.vocab_size, d), "bf16")
+    take((-1, "embed"), (embed_rows or spec.vocab_size, d), "bf16")
     for l in range(spec.n_layers):
         take((l, "attn_norm"), (d,), "f32")
         take((l, "wqkv"), (qkv, d), "bf16")
@@ -74,9 +88,9 @@ def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
 
 
 class BlobWriter:
-    def __init__(self, spec: ModelSpec):
+    def __init__(self, spec: ModelSpec, embed_rows: int | None = None):
         self.spec = spec
-        self.layout = blob_layout(spec)
+        self.layout = blob_layout(spec, embed_rows)
         self.buf = np.zeros(self.layout.total, dtype=np.uint8)
 
     def put(self, layer: int, name: str, value: np.ndarray) -> None:
@@ -103,4 +117,40 @@ def interleave_gate_up(gate: np.ndarray, up: np.ndarray) -> np.ndarray:
     out = np.empty((2 * gate.shape[0], gate.shape[1]), dtype=np.float32)
     out[0::2] = gate
     out[1::2] = up
+    return out
+
+
+def shard_blob(full: np.ndarray, spec: ModelSpec, tp_rank: int, tp_size: int) -> np.ndarray:
+    """Rank `tp_rank`'s weight blob cut out of the whole model's blob, byte for byte (no re-rounding):
+    q/k/v rows of its heads, the matching wo columns, its gate/up row pairs and wd columns, its
+    lm_head rows; norm vectors and the embedding table whole (include/advspec_engine.h)."""
+    if tp_size == 1:
+        return full
+    loc = tp_local_spec(spec, tp_size)
+    src, dst = blob_layout(spec), blob_layout(loc, spec.vocab_size)
+    out = np.zeros(dst.total, dtype=np.uint8)
+
+    def view(buf, lay, key):
+        off, shape, kind = lay.offsets[key]
+        n = int(np.prod(shape))
+        dt = np.uint16 if kind == "bf16" else np.float32
+        return buf[off: off + n * (2 if kind == "bf16" else 4)].view(dt).reshape(shape)
+
+    r, dh = tp_rank, spec.head_dim
+    hl, kl, fl, vl = loc.n_heads * dh, loc.n_kv_heads * dh, loc.d_ff, loc.vocab_size
+    hq, hk = spec.n_heads * dh, spec.n_kv_heads * dh
+    qkv_rows = np.concatenate([np.arange(r * hl, (r + 1) * hl), hq + np.arange(r * kl, (r + 1) * kl),
+                               hq + hk + np.arange(r * kl, (r + 1) * kl)])
+    view(out, dst, (-1, "embed"))[...] = view(full, src, (-1, "embed"))
+    view(out, dst, (-1, "final_norm"))[...] = view(full, src, (-1, "final_norm"))
+    view(out, dst, (-1, "lm_head"))[...] = view(full, src, (-1, "lm_head"))[r * vl:(r + 1) * vl]
+    for l in range(spec.n_layers):
+        for name in ("attn_norm", "mlp_norm"):
+            view(out, dst, (l, name))[...] = view(full, src, (l, name))
+        view(out, dst, (l, "wqkv"))[...] = view(full, src, (l, "wqkv"))[qkv_rows]
+        if spec.qkv_bias:
+            view(out, dst, (l, "bqkv"))[...] = view(full, src, (l, "bqkv"))[qkv_rows]
+        view(out, dst, (l, "wo"))[...] = view(full, src, (l, "wo"))[:, r * hl:(r + 1) * hl]
+        view(out, dst, (l, "wgu"))[...] = view(full, src, (l, "wgu"))[2 * r * fl:2 * (r + 1) * fl]
+        view(out, dst, (l, "wd"))[...] = view(full, src, (l, "wd"))[:, r * fl:(r + 1) * fl]
     return out

@@ -65,8 +65,8 @@ typedef struct advspec_model_desc {
   int32_t max_prefix_tokens;  /* capacity of one shared-prefix KV region */
   int32_t max_new_tokens;     /* capacity of one opponent's private KV suffix */
   int32_t max_seqs;           /* max opponents decoded together (<= 8) */
-  int32_t tp_rank;            /* reserved: must be 0 */
-  int32_t tp_size;            /* reserved: must be 1 */
+  int32_t tp_rank;            /* tensor parallelism: this handle's rank ... */
+  int32_t tp_size;            /* ... of 1, 2, 4 or 8 (one process per GPU); see advspec_tp_init */
   float rope_theta;
   float norm_eps;
   float embed_scale;          /* 1.0, or sqrt(d_model) for Gemma */
@@ -107,6 +107,26 @@ advspec_status advspec_engine_create(const advspec_model_desc *desc,
                                      int32_t device, advspec_engine **out);
 void advspec_engine_destroy(advspec_engine *e);
 const char *advspec_last_error(const advspec_engine *e);
+
+/* ---- tensor parallelism (one large opponent over tp_size GPUs) ----
+ * The reference has no counterpart (a remote provider hides its own sharding behind
+ * models.py:628).  `desc` always describes the WHOLE model; a handle created with
+ * tp_size > 1 holds rank tp_rank's share: n_heads/tp query heads and n_kv_heads/tp KV
+ * heads (wqkv rows, wo columns), d_ff/tp MLP columns (wgu rows, wd columns) and
+ * vocab_size/tp rows of lm_head; norm vectors and the embedding table are whole.
+ * advspec_weight_blob_bytes / advspec_weight_offset answer for that share.
+ * advspec_get_logits / advspec_prefill_logits return the rank's vocab_size/tp columns.
+ * Every rank makes the same calls with the same tokens and seeds; the ranks exchange
+ * the residual stream (all-reduce after o-proj and down-proj) and the sampler's
+ * per-rank winners (all-gather) over NCCL on the engine's stream, and return
+ * identical tokens.
+ *
+ * advspec_tp_unique_id: rank 0 obtains the 128-byte NCCL id and hands it to the other
+ * ranks by any means (the host layer uses torch.distributed).  advspec_tp_init: called
+ * on every rank's handle, concurrently; blocks until all tp_size ranks have joined.
+ * NCCL is loaded at run time (libnccl.so.2, or the path in ADVSPEC_NCCL_LIB). */
+advspec_status advspec_tp_unique_id(uint8_t *out128);
+advspec_status advspec_tp_init(advspec_engine *e, const uint8_t *id128);
 
 /* Copy a host weight blob (bf16 matrices, fp32 norm/bias vectors) to HBM. */
 advspec_status advspec_load_weights(advspec_engine *e, const void *host_blob,

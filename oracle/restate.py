@@ -36,9 +36,11 @@ def _bf16(x: torch.Tensor, on: bool) -> torch.Tensor:
 
 
 class BlobModel:
-    def __init__(self, spec: ModelSpec, blob: np.ndarray, inv_freq: np.ndarray | None = None):
+    def __init__(self, spec: ModelSpec, blob: np.ndarray, inv_freq: np.ndarray | None = None,
+                 embed_rows: int | None = None):
+        """`embed_rows`: set when `spec`/`blob` are one tensor-parallel rank's share (weights.shard_blob)."""
         self.spec = spec
-        lay = blob_layout(spec)
+        lay = blob_layout(spec, embed_rows)
         assert blob.nbytes == lay.total
         self.t: dict = {}
         for (l, name), (off, shape, kind) in lay.offsets.items():
@@ -67,8 +69,20 @@ class BlobModel:
         return torch.cat([a * cos - b * sin, b * cos + a * sin], dim=-1)
 
     @torch.no_grad()
-    def forward_logits(self, tokens, engine_rounding: bool = False) -> np.ndarray:
+    def forward_logits(self, tokens, engine_rounding: bool = False, tp_rank: int = 0, allreduce=None) -> np.ndarray:
+        """With `allreduce` (in-place sum over ranks of a tensor) this is ONE tensor-parallel rank's
+        computation as include/advspec_engine.h states it: `self` holds the rank's share, the partial
+        o-proj / down-proj products are summed across ranks with rank 0's partial carrying the residual,
+        and the result is the rank's vocabulary shard of the logits."""
         s, r = self.spec, engine_rounding
+
+        def row_split(x, partial):
+            if allreduce is None:
+                return x + partial
+            y = (x + partial) if tp_rank == 0 else partial.clone()
+            allreduce(y)
+            return y
+
         n = len(tokens)
         ids = torch.tensor(list(tokens), dtype=torch.long)
         x = self.t[(-1, "embed")][ids] * np.float32(s.embed_scale)
@@ -90,13 +104,13 @@ class BlobModel:
             sc = torch.einsum("qhd,khd->hqk", q, k) / math.sqrt(Dh) + mask
             att = torch.einsum("hqk,khd->qhd", sc.softmax(-1), v).reshape(n, H * Dh)
             att = _bf16(att, r)
-            x = x + att @ self.t[(l, "wo")].T
+            x = row_split(x, att @ self.t[(l, "wo")].T)
             xn = _bf16(self.rmsnorm(x, self.t[(l, "mlp_norm")]), r)
             gu = xn @ self.t[(l, "wgu")].T
             g, u = gu[:, 0::2], gu[:, 1::2]
             act = torch.nn.functional.gelu(g, approximate="tanh") if s.act == 1 else torch.nn.functional.silu(g)
             h = _bf16(act * u, r)
-            x = x + h @ self.t[(l, "wd")].T
+            x = row_split(x, h @ self.t[(l, "wd")].T)
         xn = _bf16(self.rmsnorm(x, self.t[(-1, "final_norm")]), r)
         head = self.t[(-1, "embed")] if s.tied_lm_head else self.t[(-1, "lm_head")]
         return (xn @ head.T).numpy()

@@ -117,3 +117,50 @@ def test_replica_prefix_broadcast_world2():
     assert pid0 == 42 and pid1 == 1048576
     assert sum0 == sum1 and sum0 > 0, "rank 1 must hold rank 0's KV bytes"
     assert ad0 is None and ad1[0] == 37 and abs(ad1[1]) < 1e-3
+
+
+# ---------------------------------------------------------------- tensor parallelism (host + sharding)
+def _tp_worker(rank, world, port, q):
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import advspec_loader
+    advspec_loader.load()
+    from advspec_b200 import model_spec, weights
+    from oracle import hf_oracle, restate
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    spec = model_spec.resolve("tiny-gqa4")
+    full = hf_oracle.export_blob(spec, hf_oracle.build_hf_model(spec, 3))
+    tokens = np.random.default_rng(1).integers(0, spec.vocab_size, 24).tolist()
+    loc = weights.tp_local_spec(spec, world)
+    shard = weights.shard_blob(full, spec, rank, world)
+    m = restate.BlobModel(loc, shard, embed_rows=spec.vocab_size)
+    mine = m.forward_logits(tokens, tp_rank=rank, allreduce=lambda t: dist.all_reduce(t))
+    parts = [torch.zeros(mine.shape) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(mine))
+    got = torch.cat(parts, dim=1).numpy()
+    if rank == 0:
+        want = restate.BlobModel(spec, full).forward_logits(tokens)
+        q.put((float(np.abs(got - want).max()), float(want.std())))
+    dist.destroy_process_group()
+
+
+def test_tensor_parallel_sharding_matches_whole_model_world2():
+    """weights.shard_blob + the exchange points stated in include/advspec_engine.h (all-reduce of the
+    residual after o-proj and down-proj, rank 0 carries the residual; logits = concatenated vocab
+    shards) reproduce the whole-model forward: two gloo ranks, restatement oracle as the arithmetic."""
+    import torch.multiprocessing as tmp
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400) + 17
+    ps = [ctx.Process(target=_tp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    err, std = q.get(timeout=120)
+    for p in ps:
+        p.join(30)
+    assert err < 1e-4 * max(std, 1.0), (err, std)
