@@ -24,7 +24,7 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("gloo")
     out = {"world": world}
-    for name in os.environ.get("TP_MODELS", "tiny-gqa4,tiny-llama-128").split(","):
+    for name in [m for m in os.environ.get("TP_MODELS", "tiny-gqa4,tiny-llama-128").split(",") if m]:
         from oracle import hf_oracle  # the checker (test infrastructure)
         spec = model_spec.resolve(name)
         model = hf_oracle.build_hf_model(spec, 11)
@@ -93,7 +93,7 @@ def main():
         e.init_weights_random(0, 0.02)
         prompt = np.random.default_rng(0).integers(0, spec.vocab_size, ptok).tolist()
         best = None
-        for rep in range(3):
+        for rep in range(int(os.environ.get("TP_REPS", "3"))):
             pid = e.prefill(prompt)
             ids = e.fork(pid, list(range(1, b + 1)))
             r = e.decode(ids, gen, temperature=0.7)
