@@ -45,6 +45,7 @@
 #include "gemv_chain.cuh"
 #include "gemv_mma.cuh"
 #include "gemv_stream.cuh"
+#include "tp_allreduce.cuh"
 
 using namespace advspec;
 
@@ -664,6 +665,12 @@ struct advspec_engine {
   int V_full = 0;  // rows of the embedding table / range of token ids (d.vocab_size is this rank's share)
   int tp_rank = 0, tp_size = 1;
   ncclComm_t comm = nullptr;
+  // decode-step exchange over peer memory (tp_allreduce.cuh): this rank's region, the peers' mappings
+  uint8_t* ar_region = nullptr;
+  uint8_t* ar_peer[kArMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned int* ar_gen = nullptr;
+  int64_t ar_max_elems = 0;
+  bool ar_ready = false;
 
   // host-side bookkeeping
   int prefix_gen = 0;     // id of the live prefix (0 = none)
@@ -764,6 +771,20 @@ advspec_status tp_allreduce(advspec_engine* e, float* buf, size_t count) {
     e->fail("tensor-parallel engine used before advspec_tp_init");
     return ADVSPEC_ERR_STATE;
   }
+  if (e->ar_ready && (int64_t)count <= e->ar_max_elems && count % 4 == 0) {
+    // latency-bound size (the decode step): push/flag/sum over NVLink peer memory, one launch
+    ArParams ap{};
+    for (int r = 0; r < e->tp_size; ++r) ap.peer[r] = e->ar_peer[r];
+    ap.data = buf;
+    ap.n = (int)count;
+    ap.tp = e->tp_size;
+    ap.rank = e->tp_rank;
+    ap.max_elems = e->ar_max_elems;
+    ap.gen = e->ar_gen;
+    E_CUDA(e, launch_pdl(tp_allreduce_kernel, dim3(kArCtas), dim3(kArThreads), 0, e->stream, true, ap));
+    e->launches++;
+    return ADVSPEC_OK;
+  }
   ncclResult_t r = g_nccl.AllReduce(buf, buf, count, ncclFloat32, ncclSum, e->comm, e->stream);
   if (r != ncclSuccess) {
     e->fail("ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
@@ -852,6 +873,10 @@ void free_all(advspec_engine* e) {
   if (e->graph) cudaGraphExecDestroy(e->graph);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   e->comm = nullptr;
+  for (int r = 0; r < kArMaxRanks; ++r)
+    if (e->ar_peer[r] && r != e->tp_rank) cudaIpcCloseMemHandle(e->ar_peer[r]);
+  if (e->ar_region) cudaFree(e->ar_region);
+  if (e->ar_gen) cudaFree(e->ar_gen);
   void* ptrs[] = {e->w, e->inv_freq, e->rope_cos, e->rope_sin, e->pkv, e->skv, e->p_tokens, e->p_x,
                   e->p_xn, e->p_qkv, e->p_attn, e->p_h, e->prefill_logits, e->dx, e->dx_save, e->dq,
                   e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->chain_bar, e->items, e->s_pos, e->kv_maps,
@@ -1456,6 +1481,57 @@ advspec_status advspec_tp_init(advspec_engine* e, const uint8_t* id128) {
     return ADVSPEC_ERR_CUDA;
   }
   E_CUDA(e, cudaStreamSynchronize(e->stream));
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_tp_ipc_export(advspec_engine* e, uint8_t* out64) {
+  if (!e || !out64) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries the CUDA IPC handle as 64 opaque bytes");
+  if (e->tp_size == 1) {
+    e->fail("advspec_tp_ipc_export on a handle without tensor parallelism");
+    return ADVSPEC_ERR_STATE;
+  }
+  E_CUDA(e, cudaSetDevice(e->device));
+  if (!e->ar_region) {
+    e->ar_max_elems = (int64_t)e->d.max_seqs * e->d.d_model;
+    const size_t bytes = kArFlagBytes + (size_t)2 * e->tp_size * e->ar_max_elems * sizeof(float);
+    E_CUDA(e, cudaMalloc(reinterpret_cast<void**>(&e->ar_region), bytes));
+    E_CUDA(e, cudaMemset(e->ar_region, 0, bytes));
+    E_CUDA(e, dmalloc(&e->ar_gen, kArCtas));
+    E_CUDA(e, cudaMemset(e->ar_gen, 0, kArCtas * sizeof(unsigned int)));
+    E_CUDA(e, cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  E_CUDA(e, cudaIpcGetMemHandle(&h, e->ar_region));
+  memcpy(out64, &h, 64);
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_tp_ipc_import(advspec_engine* e, const uint8_t* handles) {
+  if (!e || !handles) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->ar_region || e->ar_ready) {
+    e->fail("advspec_tp_ipc_import needs one prior advspec_tp_ipc_export on this handle");
+    return ADVSPEC_ERR_STATE;
+  }
+  E_CUDA(e, cudaSetDevice(e->device));
+  for (int r = 0; r < e->tp_size; ++r) {
+    if (r == e->tp_rank) {
+      e->ar_peer[r] = e->ar_region;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * 64, 64);
+    void* ptr = nullptr;
+    cudaError_t ce = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (ce != cudaSuccess) {
+      e->fail("cudaIpcOpenMemHandle for rank %d failed: %s", r, cudaGetErrorString(ce));
+      return ADVSPEC_ERR_CUDA;
+    }
+    e->ar_peer[r] = static_cast<uint8_t*>(ptr);
+  }
+  e->ar_ready = getenv("ADVSPEC_TP_NCCL_ONLY") == nullptr;
   return ADVSPEC_OK;
 }
 

@@ -74,6 +74,7 @@ class Timing(C.Structure):
 EXPORTED_SYMBOLS = [
     "advspec_weight_blob_bytes", "advspec_weight_offset", "advspec_engine_create",
     "advspec_engine_destroy", "advspec_last_error", "advspec_tp_unique_id", "advspec_tp_init",
+    "advspec_tp_ipc_export", "advspec_tp_ipc_import",
     "advspec_load_weights",
     "advspec_init_weights_random", "advspec_set_rope_inv_freq", "advspec_prefill", "advspec_fork",
     "advspec_decode", "advspec_decode_step", "advspec_get_logits", "advspec_prefill_logits",
@@ -106,6 +107,8 @@ def load_library() -> C.CDLL:
         "advspec_last_error": (C.c_char_p, [vp]),
         "advspec_tp_unique_id": (i32, [P(C.c_uint8)]),
         "advspec_tp_init": (i32, [vp, P(C.c_uint8)]),
+        "advspec_tp_ipc_export": (i32, [vp, P(C.c_uint8)]),
+        "advspec_tp_ipc_import": (i32, [vp, P(C.c_uint8)]),
         "advspec_load_weights": (i32, [vp, vp, sz]),
         "advspec_init_weights_random": (i32, [vp, C.c_uint64, f32]),
         "advspec_set_rope_inv_freq": (i32, [vp, P(f32), i32]),
@@ -216,6 +219,19 @@ class Engine:
             raise ValueError("the NCCL unique id is 128 bytes")
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._check(self.lib.advspec_tp_init(self.h, buf))
+
+    def tp_ipc_export(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._check(self.lib.advspec_tp_ipc_export(self.h, buf))
+        return bytes(buf)
+
+    def tp_ipc_import(self, handles: Sequence[bytes]) -> None:
+        """`handles`: every rank's tp_ipc_export() in rank order."""
+        raw = b"".join(handles)
+        if len(raw) != 64 * self.tp_size:
+            raise ValueError("one 64-byte handle per rank")
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        self._check(self.lib.advspec_tp_ipc_import(self.h, buf))
 
     # -- weights -----------------------------------------------------------
     def load_weights(self, blob: np.ndarray) -> None:

@@ -77,6 +77,15 @@ def create_tp_engine(spec: ModelSpec, device: int, max_prefix_tokens: int, max_n
         buf = buf.cuda(device)
     dist.broadcast(buf, src=0)
     e.tp_init(bytes(buf.cpu().numpy().tobytes()))
+    if os.environ.get("ADVSPEC_TP_NCCL_ONLY") is None:
+        # decode-step exchange over NVLink peer memory: gather every rank's CUDA IPC handle
+        mine = torch.frombuffer(bytearray(e.tp_ipc_export()), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda(device)
+        allh = [torch.zeros_like(mine) for _ in range(tp_size)]
+        dist.all_gather(allh, mine)
+        e.tp_ipc_import([bytes(h.cpu().numpy().tobytes()) for h in allh])
+        dist.barrier()  # nobody pushes before everybody has mapped
     return e
 
 

@@ -127,6 +127,15 @@ const char *advspec_last_error(const advspec_engine *e);
  * NCCL is loaded at run time (libnccl.so.2, or the path in ADVSPEC_NCCL_LIB). */
 advspec_status advspec_tp_unique_id(uint8_t *out128);
 advspec_status advspec_tp_init(advspec_engine *e, const uint8_t *id128);
+/* Optional, after advspec_tp_init: the decode step's residual exchange (b x d_model floats, 2 per
+ * layer per token: latency-bound) runs as ONE kernel over NVLink peer memory instead of through NCCL
+ * (push to every peer, flag, sum in rank order; csrc/tp_allreduce.cuh).  advspec_tp_ipc_export
+ * allocates this rank's exchange region and returns its 64-byte CUDA IPC handle; the host layer
+ * gathers the tp_size handles in rank order and gives all of them to advspec_tp_ipc_import on every
+ * rank (own entry ignored).  No rank may start a decode before every rank has imported.  Without
+ * these two calls (or with ADVSPEC_TP_NCCL_ONLY set) every exchange goes through NCCL. */
+advspec_status advspec_tp_ipc_export(advspec_engine *e, uint8_t *out64);
+advspec_status advspec_tp_ipc_import(advspec_engine *e, const uint8_t *handles);
 
 /* Copy a host weight blob (bf16 matrices, fp32 norm/bias vectors) to HBM. */
 advspec_status advspec_load_weights(advspec_engine *e, const void *host_blob,
