@@ -8,6 +8,8 @@ import advspec_loader; advspec_loader.load()
 from advspec_b200 import models, runtime, model_spec
 from advspec_b200.tokenizer import SyntheticTokenizer, generate_spec
 
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("ADVSPEC_TP"):
+    os.environ["ADVSPEC_DEVICES"] = os.environ.get("LOCAL_RANK", "0")  # one rank of a tensor-parallel group
 os.environ.setdefault("ADVSPEC_DEVICES", "0")
 gen = int(os.environ.get("CFG_GEN", "32"))
 os.environ["ADVSPEC_MAX_NEW_TOKENS"] = str(gen)
@@ -34,7 +36,8 @@ def run(name, panel, spec_tokens, doc_type, rounds=1):
                for k, v in runtime.POOL._engines.items()}
         out["rounds"].append({"round": r, "wall_s": round(wall, 3), "tokens_per_s": round(sum(x.output_tokens for x in res) / wall, 1),
                               "results": rows, "engines": eng})
-    print(json.dumps(out), flush=True)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps(out), flush=True)
     runtime.POOL.close()
 
 
@@ -46,3 +49,9 @@ if "replica16k" in which:
         ["b200/llama-3-8b"] * 4, 16384, "tech", rounds=2)
 if "long32k" in which:
     run("32K-token spec, one Llama-3-8B opponent (4 prefill chunks)", ["b200/llama-3-8b"], 32768, "tech")
+if "tp" in which:
+    # config 5 through the public API: torchrun, one process per GPU, ADVSPEC_TP = WORLD_SIZE; every rank
+    # makes the same call and gets the same critique
+    m = os.environ.get("CFG_TP_MODEL", "llama-3-8b")
+    run(f"config5-style: one {m} opponent tensor-parallel over {os.environ.get('WORLD_SIZE', '1')} GPUs",
+        [f"b200/{m}"], int(os.environ.get("CFG_TP_SPEC", "4096")), "tech")
