@@ -39,6 +39,7 @@ struct AttnDecode2Params {
   int b, H, Hkv, G;
   int opg, n_og, n_splits, n_slots;  // opponents per group, groups per KV head, prefix splits, n_splits+1
   float scale;
+  int dh;                    // head_dim in GLOBAL memory (<= DH): Phi-3's 96 runs in the 128-wide tile, zero-padded
 };
 
 template <int DH, int NST>
@@ -62,8 +63,9 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2, w4 = warp & 3;  // two warp groups take alternate key tiles
   const int g = lane >> 2, t4 = lane & 3;
-  const int QKV = (p.H + 2 * p.Hkv) * DH;
-  constexpr int half = DH / 2;
+  const int dhg = p.dh;  // global head_dim; tile columns >= dhg are zero (TMA out-of-bounds fill / zfill)
+  const int QKV = (p.H + 2 * p.Hkv) * dhg;
+  const int half = dhg / 2;
   auto swz = [](int row, int chunk) { return row * DH + ((chunk ^ (row & 7)) << 3); };  // query tile
   // K/V tiles: element offset of 16-byte chunk `chunk` (8 dims) of token row `row` in the layout TMA
   // writes with CU_TENSOR_MAP_SWIZZLE_128B: half tiles of [64 tokens][64 dims], chunk index XOR (row % 8)
@@ -90,8 +92,8 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   const __nv_bfloat16 *kb, *vb;
   int tb, te;
   if (is_prefix) {
-    kb = p.pk + (int64_t)hk * p.pstride * DH;
-    vb = p.pv + (int64_t)hk * p.pstride * DH;
+    kb = p.pk + (int64_t)hk * p.pstride * dhg;
+    vb = p.pv + (int64_t)hk * p.pstride * dhg;
     tb = (int)((int64_t)p.prefix_len * j / p.n_splits);
     te = (int)((int64_t)p.prefix_len * (j + 1) / p.n_splits);
   } else {
@@ -100,18 +102,18 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     const int bi = o0 + (j - p.n_splits);
     const int pos = p.pos_b[bi];
     const int t = pos - p.prefix_len;
-    const int64_t base = ((int64_t)p.slots[bi] * p.Hkv + hk) * p.sstride * DH;
-    __nv_bfloat16* kdst = p.sk + base + (int64_t)t * DH;
-    __nv_bfloat16* vdst = p.sv + base + (int64_t)t * DH;
-    const __nv_bfloat16* ksrc = p.qkv + (int64_t)bi * QKV + (p.H + hk) * DH;
-    const __nv_bfloat16* vsrc = p.qkv + (int64_t)bi * QKV + (p.H + p.Hkv + hk) * DH;
+    const int64_t base = ((int64_t)p.slots[bi] * p.Hkv + hk) * p.sstride * dhg;
+    __nv_bfloat16* kdst = p.sk + base + (int64_t)t * dhg;
+    __nv_bfloat16* vdst = p.sv + base + (int64_t)t * dhg;
+    const __nv_bfloat16* ksrc = p.qkv + (int64_t)bi * QKV + (p.H + hk) * dhg;
+    const __nv_bfloat16* vsrc = p.qkv + (int64_t)bi * QKV + (p.H + p.Hkv + hk) * dhg;
     for (int jj = tid; jj < half; jj += 256) {
       const float c = p.rope_cos[(int64_t)pos * half + jj], s = p.rope_sin[(int64_t)pos * half + jj];
       const float a = __bfloat162float(ksrc[jj]), bb = __bfloat162float(ksrc[jj + half]);
       kdst[jj] = __float2bfloat16_rn(a * c - bb * s);
       kdst[jj + half] = __float2bfloat16_rn(bb * c + a * s);
     }
-    for (int jj = tid; jj < DH; jj += 256) vdst[jj] = vsrc[jj];
+    for (int jj = tid; jj < dhg; jj += 256) vdst[jj] = vsrc[jj];
     __threadfence_block();
     kb = p.sk + base;
     vb = p.sv + base;
@@ -141,8 +143,8 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     } else {
       for (int id = tid; id < BN * CPR; id += 256) {
         const int r = id / CPR, c = id % CPR;
-        const bool ok = (k0 + r) < te;
-        const int64_t off = (int64_t)(ok ? k0 + r : tb) * DH + c * 8;
+        const bool ok = (k0 + r) < te && c * 8 < dhg;
+        const int64_t off = (int64_t)(ok ? k0 + r : tb) * dhg + (ok ? c * 8 : 0);
         cp_async16(dK + kvz(r, c), kb + off, ok);
         cp_async16(dV + kvz(r, c), vb + off, ok);
       }
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
       const int gr = row_off + r;
       const int bi = o0 + gr / p.G, head = hk * p.G + gr % p.G;
       const int pos = p.pos_b[bi];
-      const __nv_bfloat16* qs = p.qkv + (int64_t)bi * QKV + head * DH + jc * 8;
+      const __nv_bfloat16* qs = p.qkv + (int64_t)bi * QKV + head * dhg + jc * 8;
       const uint4 a4 = *reinterpret_cast<const uint4*>(qs);
       const uint4 b4 = *reinterpret_cast<const uint4*>(qs + half);
       const float4 c0 = *reinterpret_cast<const float4*>(p.rope_cos + (int64_t)pos * half + jc * 8);
@@ -191,6 +193,10 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     }
     *reinterpret_cast<uint4*>(sQ + swz(r, jc)) = lo;
     *reinterpret_cast<uint4*>(sQ + swz(r, jc + half / 8)) = hi;
+  }
+  for (int i = tid; i < 16 * (CPR - dhg / 8); i += 256) {  // padding columns of the query tile
+    const int r = i / (CPR - dhg / 8), c = dhg / 8 + i % (CPR - dhg / 8);
+    *reinterpret_cast<uint4*>(sQ + swz(r, c)) = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();  // sQ complete; the appended k/v row is visible to this CTA's loads
   if (!is_prefix) {
@@ -337,15 +343,15 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     s_ML[2 * tid + 1] = L;
   }
   __syncthreads();
-  for (int idx = tid; idx < n_rows * DH; idx += 256) {
-    const int r = idx / DH, d = idx % DH;
+  for (int idx = tid; idx < n_rows * dhg; idx += 256) {
+    const int r = idx / dhg, d = idx % dhg;
     float O = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) O += s_o[(w * 16 + r) * OP + d] * s_c[w * 16 + r];
     const int gr = row_off + r;
     const int bi = o0 + gr / p.G, head = hk * p.G + gr % p.G;
     const int64_t ps = ((int64_t)bi * p.H + head) * p.n_slots + slot_out;
-    p.part_o[ps * DH + d] = O;
+    p.part_o[ps * dhg + d] = O;
     if (d == 0) {
       p.part_m[ps] = s_ML[2 * r];
       p.part_l[ps] = s_ML[2 * r + 1];

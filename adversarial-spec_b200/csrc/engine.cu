@@ -580,7 +580,7 @@ int g_attn_impl = 2;  // 2: fused tensor-core decode attention (default); 1: sca
 cudaError_t launch_attn_decode2(const AttnDecode2Params& p, int n_ctas, int DH, cudaStream_t st, bool pdl) {
   constexpr int NST = 6;
   dim3 g(n_ctas), blk(256);
-  if (DH == 128) {
+  if (DH == 128 || DH == 96) {  // 96 (Phi-3): the 128-wide tile with zero padding, p.dh = 96
     const int smem = 16 * 128 * 2 + NST * 2 * 64 * 128 * 2 + 1024 + 128;  // + alignment slack + barriers
     {  // function attributes are per device: set on every launch (host-side, microseconds)
       cudaError_t e = set_smem(attn_decode_mma_kernel<128, NST>, smem);
@@ -950,8 +950,11 @@ void plan_attn2(advspec_engine* e, const std::vector<int>& slots) {
   const int opg = std::max(1, 16 / G);
   const int n_og = (b + opg - 1) / opg;
   const int groups = d.n_kv_heads * n_og;
+  // one wave of CTAs when that still cuts the prefix at least in two (GQA models); with many KV heads
+  // (MHA: Phi-3 has 32) the prefix CTAs alone fill the wave and the short per-opponent suffix CTAs trail
   const int slots_left = std::max(groups, num_sms(e->device) - b * d.n_kv_heads);
   int n_splits = std::max(1, slots_left / std::max(1, groups));
+  if (n_splits < 2) n_splits = std::max(1, num_sms(e->device) / std::max(1, groups));
   n_splits = std::min(n_splits, std::max(1, e->prefix_len / g_attn_min_split));
   n_splits = std::min(n_splits, 300);
   e->a2_opg = opg;
@@ -1050,6 +1053,7 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       a2.n_splits = e->a2_n_splits;
       a2.n_slots = e->n_slots;
       a2.scale = 1.0f / sqrtf((float)d.head_dim);
+      a2.dh = d.head_dim;
       E_CUDA(e, launch_attn_decode2(a2, e->a2_ctas, d.head_dim, e->stream, true));
       ADV_TRACE(e->stream, "attn_decode_mma");
       E_CUDA(e, launch_pdl(attn_decode_combine2_kernel, dim3(b * d.n_heads), dim3(128), 0, e->stream, true,
@@ -1361,7 +1365,8 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, cudaMemsetAsync(e->chain_bar, 0, 4 * sizeof(unsigned int), e->stream));
     E_CUDA(e, dmalloc(&e->s_pos, B));
     E_CUDA(e, cudaMemsetAsync(e->s_pos, 0, B * sizeof(int), e->stream));
-    e->attn_fused = g_attn_impl == 2 && (d.head_dim == 64 || d.head_dim == 128) && G <= 16 && d.n_heads <= 255;
+    e->attn_fused = g_attn_impl == 2 && (d.head_dim == 64 || d.head_dim == 96 || d.head_dim == 128) && G <= 16 &&
+                    d.n_heads <= 255;
     if (e->attn_fused) {
       std::vector<CUtensorMap> hm((size_t)d.n_layers * 2);
       for (int l = 0; l < d.n_layers; ++l) {
