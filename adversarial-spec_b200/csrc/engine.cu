@@ -588,6 +588,15 @@ cudaError_t launch_attn_decode2(const AttnDecode2Params& p, int n_ctas, int DH, 
     }
     return launch_pdl(attn_decode_mma_kernel<128, NST>, g, blk, smem, st, pdl, p);
   }
+  if (DH == 256) {  // Gemma: 64 KB per K+V tile pair, three stages
+    constexpr int NS3 = 3;
+    const int smem = 16 * 256 * 2 + NS3 * 2 * 64 * 256 * 2 + 1024 + 128;
+    {
+      cudaError_t e = set_smem(attn_decode_mma_kernel<256, NS3>, smem);
+      if (e != cudaSuccess) return e;
+    }
+    return launch_pdl(attn_decode_mma_kernel<256, NS3>, g, blk, smem, st, pdl, p);
+  }
   if (DH == 64) {
     const int smem = 16 * 64 * 2 + NST * 2 * 64 * 64 * 2 + 1024 + 128;
     {  // function attributes are per device: set on every launch (host-side, microseconds)
@@ -1365,7 +1374,7 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, cudaMemsetAsync(e->chain_bar, 0, 4 * sizeof(unsigned int), e->stream));
     E_CUDA(e, dmalloc(&e->s_pos, B));
     E_CUDA(e, cudaMemsetAsync(e->s_pos, 0, B * sizeof(int), e->stream));
-    e->attn_fused = g_attn_impl == 2 && (d.head_dim == 64 || d.head_dim == 96 || d.head_dim == 128) && G <= 16 &&
+    e->attn_fused = g_attn_impl == 2 && (d.head_dim == 64 || d.head_dim == 96 || d.head_dim == 128 || d.head_dim == 256) && G <= 16 &&
                     d.n_heads <= 255;
     if (e->attn_fused) {
       std::vector<CUtensorMap> hm((size_t)d.n_layers * 2);
