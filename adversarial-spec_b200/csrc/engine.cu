@@ -1309,19 +1309,27 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   e->use_graph = getenv("ADVSPEC_NO_GRAPH") == nullptr;
   g_use_pdl = getenv("ADVSPEC_NO_PDL") == nullptr;
   g_trace = getenv("ADVSPEC_TRACE") != nullptr;
-  if (const char* gi = getenv("ADVSPEC_GEMV_IMPL")) g_gemv_impl = std::max(1, std::min(3, atoi(gi)));
-  if (const char* ai = getenv("ADVSPEC_ATTN_IMPL")) g_attn_impl = atoi(ai) == 1 ? 1 : 2;
-  if (const char* xm = getenv("ADVSPEC_X_SMEM_MAX")) g_x_smem_max = (size_t)atoll(xm);
+  // process-wide A/B knobs are re-read at every create (unset = default), so one process can compare them
+  const char* gi = getenv("ADVSPEC_GEMV_IMPL");
+  g_gemv_impl = gi ? std::max(1, std::min(3, atoi(gi))) : 3;
+  const char* ai = getenv("ADVSPEC_ATTN_IMPL");
+  g_attn_impl = (ai && atoi(ai) == 1) ? 1 : 2;
+  const char* xm = getenv("ADVSPEC_X_SMEM_MAX");
+  g_x_smem_max = xm ? (size_t)atoll(xm) : 40000;
   g_gemm_narrow = getenv("ADVSPEC_GEMM_NARROW") != nullptr;
-  if (const char* tc = getenv("ADVSPEC_ATTN_PREFILL_TC")) g_attn_prefill_tc = atoi(tc) != 0;
-  if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
-  if (const char* ch = getenv("ADVSPEC_CHAIN")) g_chain = atoi(ch) != 0;
+  const char* tc = getenv("ADVSPEC_ATTN_PREFILL_TC");
+  g_attn_prefill_tc = tc ? atoi(tc) != 0 : true;
+  const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT");
+  g_attn_min_split = ms ? std::max(64, atoi(ms)) : 256;
+  const char* ch = getenv("ADVSPEC_CHAIN");
+  g_chain = ch ? atoi(ch) != 0 : 0;
 
   auto boot = [&]() -> advspec_status {
     const auto& d = e->d;
     E_CUDA(e, cudaSetDevice(device));
-    if (const char* ef = getenv("ADVSPEC_L2_EVICT_FIRST")) {
-      const int v = atoi(ef);
+    {
+      const char* ef = getenv("ADVSPEC_L2_EVICT_FIRST");
+      const int v = ef ? atoi(ef) : 1;
       E_CUDA(e, cudaMemcpyToSymbol(g_l2_evict_first, &v, sizeof v));
     }
     E_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));

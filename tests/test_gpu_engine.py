@@ -281,3 +281,40 @@ def test_eos_stops_one_opponent_only(cuda_device):
     e.close()
     assert got.tokens == want and got.lens == [len(w) for w in want]
     assert got.lens[0] <= 4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"ADVSPEC_CHAIN": "1"}, {"ADVSPEC_L2_EVICT_FIRST": "0"}, {"ADVSPEC_NO_PDL": "1"},
+                                 {"ADVSPEC_ATTN_IMPL": "1"}])
+def test_opt_in_decode_variants_give_the_default_logits(cuda_device, diag, monkeypatch, env):
+    """The A/B knobs of DESIGN.md §4 (persistent GEMV chain, L2 policy, no programmatic launch, the
+    scalar decode attention) change scheduling, not arithmetic: teacher-forced decode logits must match
+    the default path within the HF tolerance, and exactly where the kernels are the same."""
+    rng = np.random.default_rng(21)
+
+    def run():
+        spec, model, e = make_engine("tiny-llama-128", 5, 512, 32, 4)
+        prompt = rng_prompt
+        pid = e.prefill(prompt)
+        ids = e.fork(pid, [1, 2, 3])
+        outs = []
+        for t in forced:
+            e.decode_step(ids, [t, t, t])
+            outs.append(e.get_logits(3).copy())
+        e.close()
+        return np.stack(outs)
+
+    spec0 = make_engine("tiny-llama-128", 5, 512, 32, 4)
+    spec0[2].close()
+    rng_prompt = rng.integers(0, spec0[0].vocab_size, 300).tolist()
+    forced = rng.integers(0, spec0[0].vocab_size, 5).tolist()
+    base = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = run()
+    mx, rms = rel_errors(got, base)
+    diag[f"decode variant {env}"] = {"max_over_std": mx, "rms_over_std": rms}
+    if "ADVSPEC_ATTN_IMPL" in env:
+        assert mx < TOL_MAX and rms < TOL_RMS
+    else:
+        assert mx == 0.0, (env, mx)
