@@ -76,6 +76,85 @@ CASES = [
 ]
 
 
+# Multi-step flows through ONE home + working directory: session create -> resume, context files.
+# The stub also records what the reference puts on the wire (wire.jsonl) so the envelope of resumed,
+# pressed and context-carrying rounds is pinned too.
+FLOW_STUB = CANNED_STUB + '''
+_orig_completion = completion
+def completion(**kw):
+    with open(os.path.join(os.environ["HOME"], "wire.jsonl"), "a") as f:
+        f.write(json.dumps({"model": kw["model"], "messages": kw["messages"],
+                            "max_tokens": kw.get("max_tokens"), "temperature": kw.get("temperature")}) + "\\n")
+    return _orig_completion(**kw)
+'''
+
+FLOWS = [
+    {"name": "session_create_then_resume",
+     "steps": [
+         {"argv": ["critique", "--models", "fake/a,fake/b", "--session", "s1", "--json", "--focus", "security"],
+          "responses": {"fake/a": {"content": "needs work\n[SPEC]\nrevised once\n[/SPEC]", "in": 40, "out": 8, "delay": 0.0},
+                        "fake/b": {"content": "fine [AGREE]", "in": 41, "out": 3, "delay": 0.3}}},
+         {"argv": ["critique", "--resume", "s1", "--models", "fake/a,fake/b", "--show-cost"], "stdin": "",
+          "responses": {"fake/a": {"content": "[AGREE]\n[SPEC]final[/SPEC]", "in": 12, "out": 4, "delay": 0.0},
+                        "fake/b": {"content": "[AGREE]", "in": 13, "out": 2, "delay": 0.3}}},
+     ]},
+    {"name": "resume_without_models_is_refused",  # model selection runs before the session is read
+     "steps": [{"argv": ["critique", "--resume", "s1"], "stdin": "",
+                "responses": {"fake/a": {"content": "x", "in": 1, "out": 1}}}]},
+    {"name": "resume_unknown_session",
+     "steps": [{"argv": ["critique", "--resume", "nope", "--models", "fake/a"], "stdin": "",
+                "responses": {"fake/a": {"content": "x", "in": 1, "out": 1}}}]},
+    {"name": "context_files_and_checkpoint",
+     "files": {"api.md": "# API\nGET /v1/things\n", "schema.sql": "create table t (id int);\n"},
+     "steps": [{"argv": ["critique", "--models", "fake/a", "--context", "api.md", "--context", "schema.sql",
+                         "--context", "missing.txt", "--session", "ctx", "--round", "2", "--doc-type", "prd"],
+                "responses": {"fake/a": {"content": "crit\n[SPEC]with context[/SPEC]", "in": 70, "out": 9}}}]},
+]
+
+
+def _snapshot(td: str) -> dict:
+    """Files the flow left behind, with timestamps and the temporary directory normalised."""
+    import re
+    out = {}
+    for pth in sorted(Path(td).rglob("*")):
+        rel = pth.relative_to(td).as_posix()
+        if not pth.is_file() or rel == "litellm.py" or "__pycache__" in rel:
+            continue
+        txt = pth.read_text()
+        txt = re.sub(r'"(created_at|updated_at|timestamp)": "[^"]*"', lambda m: '"%s": "<ts>"' % m.group(1), txt)
+        txt = txt.replace(td, "<DIR>")
+        out[rel] = txt
+    return out
+
+
+def run_reference_flow(flow: dict) -> dict:
+    steps = []
+    with tempfile.TemporaryDirectory() as td:
+        (Path(td) / "litellm.py").write_text(FLOW_STUB)
+        for name, content in flow.get("files", {}).items():
+            (Path(td) / name).write_text(content)
+        for step in flow["steps"]:
+            env = {k: v for k, v in os.environ.items() if not k.endswith("_API_KEY")}
+            env.update(PYTHONPATH=td, ADVSPEC_CANNED=json.dumps(step), HOME=td)
+            p = subprocess.run([sys.executable, str(REF_SCRIPTS / "debate.py"), *step["argv"]],
+                               input=step.get("stdin", SPEC_TEXT), capture_output=True, text=True, env=env, cwd=td)
+            steps.append({"stdout": p.stdout.replace(td, "<DIR>"), "stderr": p.stderr.replace(td, "<DIR>"),
+                          "returncode": p.returncode})
+        snap = _snapshot(td)
+    return {"steps": steps, "files": snap}
+
+
+def make_reference_flows() -> None:
+    out = []
+    for flow in FLOWS:
+        got = run_reference_flow(flow)
+        for st in flow["steps"]:
+            st.setdefault("stdin", SPEC_TEXT)
+        out.append({**flow, "expected": got})
+        print(f"flow {flow['name']}: rcs={[s['returncode'] for s in got['steps']]} files={sorted(got['files'])}")
+    (GOLDEN / "reference_cli_flows.json").write_text(json.dumps(out, indent=1))
+
+
 def run_reference_cli(case: dict) -> dict:
     with tempfile.TemporaryDirectory() as td:
         (Path(td) / "litellm.py").write_text(CANNED_STUB)
@@ -164,6 +243,7 @@ if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
     if REF_SCRIPTS.exists():
         make_reference_cases()
+        make_reference_flows()
         make_message_fixtures()
     else:
         print("no /root/reference here: reference fixtures left untouched")
