@@ -612,9 +612,6 @@ __global__ void advance_kernel(const int* slots, int* suf_len) {
   pdl_wait();
   suf_len[slots[threadIdx.x]] += 1;
 }
-__global__ void copy_logits_kernel(const float* src, float* dst, int V) {
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) dst[v] = src[v];
-}
 
 }  // namespace
 

@@ -13,6 +13,7 @@ pointer to the reference CLI.
 from __future__ import annotations
 
 import argparse
+import os
 import json
 import sys
 from datetime import datetime
@@ -243,7 +244,21 @@ def handle_export_tasks(args, models: list[str]) -> None:
         sys.exit(1)
 
 
+def _tensor_parallel_follower() -> bool:
+    """Under `torchrun` with ADVSPEC_TP=k every rank runs this CLI with the same arguments and stdin (the
+    ranks of one tensor-parallel engine make identical calls); only rank 0 reports and writes files."""
+    try:
+        return int(os.environ.get("ADVSPEC_TP", "1")) > 1 and int(os.environ.get("RANK", "0")) != 0
+    except ValueError:
+        return False
+
+
 def main() -> None:
+    if _tensor_parallel_follower():
+        sink = open(os.devnull, "w")
+        sys.stdout = sys.stderr = sink
+        _session.SessionState.save = lambda self: None
+        globals()["save_checkpoint"] = lambda *a, **k: None
     args = create_parser().parse_args()
     if args.action == "providers":
         _providers.list_providers()

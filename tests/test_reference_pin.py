@@ -98,6 +98,7 @@ def test_extract_tasks_agrees_with_reference_on_random_blocks():
     with tempfile.TemporaryDirectory() as td:
         Path(td, "litellm.py").write_text("suppress_debug_info=False\ndef completion(**k):\n    raise RuntimeError\n")
         sys.path[:0] = [td, "/root/reference/skills/adversarial-spec/scripts"]
+        before = set(sys.modules)
         try:
             spec = importlib.util.spec_from_file_location("_ref_models", "/root/reference/skills/adversarial-spec/scripts/models.py")
             ref = importlib.util.module_from_spec(spec)
@@ -105,6 +106,8 @@ def test_extract_tasks_agrees_with_reference_on_random_blocks():
             spec.loader.exec_module(ref)
         finally:
             del sys.path[:2]
+            for k in set(sys.modules) - before - {"_ref_models"}:
+                del sys.modules[k]  # the stub `litellm` and the reference's prompts/providers must not leak
     rng = random.Random(0)
     lines = ["title: A", "title:", "type: bug", "priority: high", "description: d1", "more text", "- item", "- ",
              "acceptance_criteria:", "acceptance_criteria: inline", "  - indented", "", "random: x", "[TASK]", "[/TASK]"]

@@ -55,3 +55,43 @@ if "tp" in which:
     m = os.environ.get("CFG_TP_MODEL", "llama-3-8b")
     run(f"config5-style: one {m} opponent tensor-parallel over {os.environ.get('WORLD_SIZE', '1')} GPUs",
         [f"b200/{m}"], int(os.environ.get("CFG_TP_SPEC", "4096")), "tech")
+if "converge16k" in which:
+    # config 4 the way the reference drives it — one `debate.py critique` per round, `--session` then
+    # `--resume` — but in ONE process, so the engine (weights, workspaces) stays resident across rounds
+    import contextlib, io, tempfile
+    from advspec_b200 import debate, session
+    rounds = int(os.environ.get("CFG_ROUNDS", "6"))
+    n_tok = int(os.environ.get("CFG_SPEC", "16384"))
+    doc = generate_spec(SyntheticTokenizer(32000), n_tok, seed=11).strip()
+    td = tempfile.mkdtemp()
+    session.SESSIONS_DIR = Path(td) / ".config" / "adversarial-spec" / "sessions"
+    session.CHECKPOINTS_DIR = Path(td) / ".adversarial-spec-checkpoints"
+    panel = ",".join(["b200/llama-3-8b"] * 4)
+    out = {"run": f"config4: 4 replicas x {rounds} rounds, {n_tok}-token tech spec, debate.py critique --session/--resume in one process",
+           "new_tokens": gen, "rounds": []}
+    for r in range(1, rounds + 1):
+        argv = ["debate.py", "critique", "--models", panel, "--doc-type", "tech", "--json"] + \
+               (["--session", "cfg4"] if r == 1 else ["--resume", "cfg4"])
+        sys.argv, sys.stdin = argv, io.StringIO(doc if r == 1 else "")
+        so, se = io.StringIO(), io.StringIO()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(so), contextlib.redirect_stderr(se):
+            try:
+                debate.main()
+                rc = 0
+            except SystemExit as e:
+                rc = e.code or 0
+        wall = time.perf_counter() - t0
+        res = json.loads(so.getvalue()) if rc == 0 else {}
+        eng = {f"{k[0]}@{k[1]}": {"prefill_ms": round(v.engine.timing().prefill_ms, 2),
+                                  "decode_ms_per_step": round(v.engine.timing().decode_ms / max(v.engine.timing().decode_steps, 1), 3),
+                                  "batch": v.engine.timing().decode_batch} for k, v in runtime.POOL._engines.items()}
+        toks = sum(x["output_tokens"] for x in res.get("results", []))
+        out["rounds"].append({"round": res.get("round"), "rc": rc, "wall_s": round(wall, 3), "output_tokens": toks,
+                              "tokens_per_s": round(toks / wall, 1), "all_agreed": res.get("all_agreed"),
+                              "input_tokens": [x["input_tokens"] for x in res.get("results", [])], "engines": eng,
+                              "stderr_first_line": se.getvalue().splitlines()[0] if se.getvalue() else ""})
+    out["session_file_rounds"] = json.loads((session.SESSIONS_DIR / "cfg4.json").read_text())["round"]
+    out["checkpoints"] = sorted(p.name for p in session.CHECKPOINTS_DIR.glob("*.md"))
+    print(json.dumps(out), flush=True)
+    runtime.POOL.close()
