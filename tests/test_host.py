@@ -3,6 +3,8 @@
 import hashlib
 import json
 import threading
+
+import numpy as np
 from pathlib import Path
 from unittest.mock import patch
 
@@ -160,3 +162,54 @@ def test_render_chat_and_budget_env(monkeypatch):
     assert runtime.effective_max_new(8000) == 8000
     assert len({runtime.opponent_seed(1, i) for i in range(8)}) == 8
     assert "tiny-llama" in REGISTRY
+
+
+@pytest.mark.parametrize("tp", [2, 4])
+def test_shard_blob_partitions_every_tensor_exactly(tp):
+    """weights.shard_blob: the ranks' shares tile the whole model's tensors without overlap or loss
+    (q/k/v rows per head range, wo / wd columns, gate/up row pairs, lm_head rows; norms and the
+    embedding table replicated), byte for byte, in the layout csrc/engine.cu computes for a rank."""
+    import ctypes as C
+
+    from advspec_b200 import engine as eng, weights
+    from advspec_b200.model_spec import ModelSpec
+
+    spec = ModelSpec("shard-test", "llama", 2, 64, 8, 4, 64, 128, 96, qkv_bias=True)
+    full_lay = weights.blob_layout(spec)
+    rng = np.random.default_rng(0)
+    full = rng.integers(0, 255, full_lay.total, dtype=np.uint8)
+
+    def view(buf, lay, key):
+        off, shape, kind = lay.offsets[key]
+        n = int(np.prod(shape)) * (2 if kind == "bf16" else 4)
+        return buf[off: off + n].view(np.uint16 if kind == "bf16" else np.uint32).reshape(shape)
+
+    loc = weights.tp_local_spec(spec, tp)
+    lay = weights.blob_layout(loc, spec.vocab_size)
+    shards = [weights.shard_blob(full, spec, r, tp) for r in range(tp)]
+    try:
+        lib = eng.load_library()
+        for r in range(tp):
+            d = eng.make_desc(spec, 64, 16, 2, r, tp)
+            assert lib.advspec_weight_blob_bytes(C.byref(d)) == shards[r].nbytes == lay.total
+    except eng.EngineError:
+        pass  # library not built: the layout agreement is covered by tests/test_abi.py
+    dh, H, Hkv = spec.head_dim, spec.n_heads, spec.n_kv_heads
+    for l in range(spec.n_layers):
+        parts = [view(s, lay, (l, "wqkv")) for s in shards]
+        hl, kl = loc.n_heads * dh, loc.n_kv_heads * dh
+        q = np.concatenate([p[:hl] for p in parts]); k = np.concatenate([p[hl:hl + kl] for p in parts])
+        v = np.concatenate([p[hl + kl:] for p in parts])
+        assert np.array_equal(np.concatenate([q, k, v]), view(full, full_lay, (l, "wqkv")))
+        b = [view(s, lay, (l, "bqkv")) for s in shards]
+        assert np.array_equal(np.concatenate([np.concatenate([p[:hl] for p in b]), np.concatenate([p[hl:hl + kl] for p in b]),
+                                              np.concatenate([p[hl + kl:] for p in b])]), view(full, full_lay, (l, "bqkv")))
+        for name, axis in (("wo", 1), ("wd", 1), ("wgu", 0)):
+            assert np.array_equal(np.concatenate([view(s, lay, (l, name)) for s in shards], axis=axis),
+                                  view(full, full_lay, (l, name)))
+        for name in ("attn_norm", "mlp_norm"):
+            assert all(np.array_equal(view(s, lay, (l, name)), view(full, full_lay, (l, name))) for s in shards)
+    assert np.array_equal(np.concatenate([view(s, lay, (-1, "lm_head")) for s in shards]), view(full, full_lay, (-1, "lm_head")))
+    assert all(np.array_equal(view(s, lay, (-1, "embed")), view(full, full_lay, (-1, "embed"))) for s in shards)
+    with pytest.raises(ValueError):
+        weights.tp_local_spec(spec, 3)
