@@ -213,3 +213,15 @@ def test_shard_blob_partitions_every_tensor_exactly(tp):
     assert all(np.array_equal(view(s, lay, (-1, "embed")), view(full, full_lay, (-1, "embed"))) for s in shards)
     with pytest.raises(ValueError):
         weights.tp_local_spec(spec, 3)
+
+
+def test_tp_world_needs_one_process_per_gpu(monkeypatch):
+    monkeypatch.delenv("ADVSPEC_TP", raising=False)
+    assert runtime.tp_world() == (0, 1)
+    monkeypatch.setenv("ADVSPEC_TP", "4")
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    with pytest.raises(RuntimeError, match="WORLD_SIZE=4"):
+        runtime.tp_world()
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    monkeypatch.setenv("RANK", "3")
+    assert runtime.tp_world() == (3, 4)
