@@ -6,7 +6,6 @@
 
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"  // epilogue enums, activations
-#include "tp_allreduce.cuh"  // ArParams: the tensor-parallel exchange fused into the row-split GEMV
 
 namespace advspec {
 
@@ -31,12 +30,7 @@ struct GemvParams {
   int N, K;
   int in_mode, epilogue, act;
   float eps;
-  ArParams tp;          // EPI_TP_RESADD only (gemv_mma_kernel): peers, rank, generation words; `y` is the residual
 };
-// GEMV-only epilogue: y (fp32 residual, replicated on every tensor-parallel rank) += sum over ranks of the
-// partial products — each CTA pushes its rows to every peer, the last CTA raises the flags, every CTA
-// sums its own rows once all ranks' flags are up (tp_allreduce.cuh describes the protocol).
-constexpr int EPI_TP_RESADD = 4;
 
 constexpr int kGemvThreads = 256;
 constexpr int kGemvWarps = 8;

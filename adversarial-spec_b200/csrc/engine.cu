@@ -677,7 +677,6 @@ struct advspec_engine {
   unsigned int* ar_gen = nullptr;
   int64_t ar_max_elems = 0;
   bool ar_ready = false;
-  bool ar_fused = false;  // the decode exchange rides in the o-proj / down-proj GEMV (EPI_TP_RESADD)
 
   // host-side bookkeeping
   int prefix_gen = 0;     // id of the live prefix (0 = none)
@@ -770,17 +769,6 @@ const __nv_bfloat16* lm_head_w(advspec_engine* e) {
 }
 const float* final_norm_w(advspec_engine* e) { return reinterpret_cast<const float*>(e->wp(e->lay.final_norm)); }
 
-ArParams make_ar_params(advspec_engine* e, float* data, size_t count) {
-  ArParams ap{};
-  for (int r = 0; r < e->tp_size; ++r) ap.peer[r] = e->ar_peer[r];
-  ap.data = data;
-  ap.n = (int)count;
-  ap.tp = e->tp_size;
-  ap.rank = e->tp_rank;
-  ap.max_elems = e->ar_max_elems;
-  ap.gen = e->ar_gen;
-  return ap;
-}
 // Tensor-parallel exchange: sum the ranks' partial residual streams in place (rank 0's partial
 // already carries the residual, so the sum is the new residual on every rank).
 advspec_status tp_allreduce(advspec_engine* e, float* buf, size_t count) {
@@ -791,7 +779,14 @@ advspec_status tp_allreduce(advspec_engine* e, float* buf, size_t count) {
   }
   if (e->ar_ready && (int64_t)count <= e->ar_max_elems && count % 4 == 0) {
     // latency-bound size (the decode step): push/flag/sum over NVLink peer memory, one launch
-    ArParams ap = make_ar_params(e, buf, count);
+    ArParams ap{};
+    for (int r = 0; r < e->tp_size; ++r) ap.peer[r] = e->ar_peer[r];
+    ap.data = buf;
+    ap.n = (int)count;
+    ap.tp = e->tp_size;
+    ap.rank = e->tp_rank;
+    ap.max_elems = e->ar_max_elems;
+    ap.gen = e->ar_gen;
     E_CUDA(e, launch_pdl(tp_allreduce_kernel, dim3(kArCtas), dim3(kArThreads), 0, e->stream, true, ap));
     e->launches++;
     return ADVSPEC_OK;
@@ -804,11 +799,6 @@ advspec_status tp_allreduce(advspec_engine* e, float* buf, size_t count) {
   e->launches++;
   return ADVSPEC_OK;
 }
-// Decode only: can the exchange ride inside the row-split GEMV itself?  (tensor-core GEMV, peer regions mapped)
-inline bool tp_fused_decode(const advspec_engine* e, int K) {
-  return e->tp_size > 1 && e->ar_fused && g_gemv_impl == 3 && K % 16 == 0;
-}
-
 // Epilogue of a row-split product (o-proj, down-proj): rank 0 adds into the residual, the other
 // ranks overwrite their copy with the bare partial; tp_allreduce follows.
 inline int tp_resadd_epi(const advspec_engine* e) {
@@ -1120,27 +1110,15 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       continue;
     }
     GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, tp_resadd_epi(e), d.act, d.norm_eps};
-    const bool fuse_o = !prof && tp_fused_decode(e, HD);
-    if (fuse_o) {
-      g2.epilogue = EPI_TP_RESADD;
-      g2.tp = make_ar_params(e, e->dx, (size_t)b * dm);
-    }
     E_CUDA(e, gemv(g2));
     ADV_TRACE(e->stream, "gemv o");
-    if (!fuse_o)
-      if (advspec_status ts = tp_allreduce(e, e->dx, (size_t)b * dm)) return ts;
+    if (advspec_status ts = tp_allreduce(e, e->dx, (size_t)b * dm)) return ts;
     GemvParams g3{w.wgu, e->dx, w.mlp_norm, nullptr, e->dh, 2 * d.d_ff, dm, 1, EPI_GATED_BF16, d.act, d.norm_eps};
     E_CUDA(e, gemv(g3));
     ADV_TRACE(e->stream, "gemv gate_up");
     GemvParams g4{w.wd, e->dh, nullptr, nullptr, e->dx, dm, d.d_ff, 0, tp_resadd_epi(e), d.act, d.norm_eps};
-    const bool fuse_d = !prof && tp_fused_decode(e, d.d_ff);
-    if (fuse_d) {
-      g4.epilogue = EPI_TP_RESADD;
-      g4.tp = make_ar_params(e, e->dx, (size_t)b * dm);
-    }
     E_CUDA(e, gemv(g4));
-    if (!fuse_d)
-      if (advspec_status ts = tp_allreduce(e, e->dx, (size_t)b * dm)) return ts;
+    if (advspec_status ts = tp_allreduce(e, e->dx, (size_t)b * dm)) return ts;
     ADV_TRACE(e->stream, "gemv down");
     e->launches += 3;
   }
@@ -1536,11 +1514,11 @@ advspec_status advspec_tp_ipc_export(advspec_engine* e, uint8_t* out64) {
   E_CUDA(e, cudaSetDevice(e->device));
   if (!e->ar_region) {
     e->ar_max_elems = (int64_t)e->d.max_seqs * e->d.d_model;
-    const size_t bytes = ar_region_bytes(e->tp_size, e->ar_max_elems);
+    const size_t bytes = kArFlagBytes + (size_t)2 * e->tp_size * e->ar_max_elems * sizeof(float);
     E_CUDA(e, cudaMalloc(reinterpret_cast<void**>(&e->ar_region), bytes));
     E_CUDA(e, cudaMemset(e->ar_region, 0, bytes));
-    E_CUDA(e, dmalloc(&e->ar_gen, kArGenWords));
-    E_CUDA(e, cudaMemset(e->ar_gen, 0, kArGenWords * sizeof(unsigned int)));
+    E_CUDA(e, dmalloc(&e->ar_gen, kArCtas));
+    E_CUDA(e, cudaMemset(e->ar_gen, 0, kArCtas * sizeof(unsigned int)));
     E_CUDA(e, cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t h;
@@ -1573,9 +1551,6 @@ advspec_status advspec_tp_ipc_import(advspec_engine* e, const uint8_t* handles) 
     e->ar_peer[r] = static_cast<uint8_t*>(ptr);
   }
   e->ar_ready = getenv("ADVSPEC_TP_NCCL_ONLY") == nullptr;
-  // exchange inside the row-split GEMV itself (EPI_TP_RESADD); ADVSPEC_TP_FUSED=0 keeps the separate kernel (A/B)
-  const char* fu = getenv("ADVSPEC_TP_FUSED");
-  e->ar_fused = e->ar_ready && fu != nullptr && atoi(fu) != 0;
   return ADVSPEC_OK;
 }
 

@@ -118,9 +118,6 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
     }
     if (p.bias != nullptr && tid * 32 < row_end - row_begin) prefetch_l2_line(p.bias + row_begin + tid * 32);
     pdl_wait();
-    // fused tensor-parallel exchange: this launch's generation (device state, read after the dependency wait)
-    const unsigned int tp_gen = (p.epilogue == EPI_TP_RESADD) ? __ldcg(&p.tp.gen[kArFusedGen]) + 1u : 0u;
-    const int tp_set = (int)(tp_gen & 1u);
     const uint8_t* xbase;  // bf16 rows of x, pitch xstride bytes
     int xstride;
     if (p.in_mode == 1) {
@@ -292,42 +289,11 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemv_mma_kernel(GemvParams p, i
             reinterpret_cast<__nv_bfloat16*>(p.y)[(int64_t)b * p.N + n] = __float2bfloat16_rn(tsum);
           } else if (p.epilogue == EPI_RESADD_F32) {
             reinterpret_cast<float*>(p.y)[(int64_t)b * p.N + n] += tsum;
-          } else if (p.epilogue == EPI_TP_RESADD) {
-            // rank 0's partial carries the residual; every rank's region gets this rank's value
-            const int64_t at = (int64_t)b * p.N + n;
-            const float v = (p.tp.rank == 0) ? tsum + __ldcg(reinterpret_cast<const float*>(p.y) + at) : tsum;
-#pragma unroll 1
-            for (int r = 0; r < p.tp.tp; ++r) ar_fused_slot(p.tp, r, tp_set, p.tp.rank)[at] = v;
           } else {
             reinterpret_cast<float*>(p.y)[(int64_t)b * p.N + n] = tsum;
           }
         }
       }
-    }
-    if (p.epilogue == EPI_TP_RESADD) {
-      // ---- exchange tail: the last CTA of this rank raises the flags on every peer; every CTA waits for
-      // all ranks' flags, then sums its own rows over the tp slots in rank order (bit-identical everywhere)
-      named_bar_sync(1, kGmConsumers);
-      if (tid == 0) {
-        __threadfence_system();  // this CTA's pushes (ordered before this thread by the barrier)
-        if (atomicAdd(&p.tp.gen[kArFusedDone], 1u) == gridDim.x - 1) {
-          p.tp.gen[kArFusedDone] = 0;
-          __threadfence_system();
-          for (int r = 0; r < p.tp.tp; ++r) st_release_sys(ar_fused_flag(p.tp, r, tp_set, p.tp.rank), tp_gen);
-        }
-      }
-      if (tid < p.tp.tp) ar_wait_flag(ar_fused_flag(p.tp, p.tp.rank, tp_set, tid), tp_gen, (unsigned)tid);
-      named_bar_sync(1, kGmConsumers);
-      float* yout = reinterpret_cast<float*>(p.y);
-      const int rows_cta = max(row_end - row_begin, 0);
-      for (int idx = tid; idx < rows_cta * B; idx += kGmConsumers) {
-        const int64_t at = (int64_t)(idx % B) * p.N + row_begin + idx / B;
-        float a = __ldcg(ar_fused_slot(p.tp, p.tp.rank, tp_set, 0) + at);
-        for (int r = 1; r < p.tp.tp; ++r) a += __ldcg(ar_fused_slot(p.tp, p.tp.rank, tp_set, r) + at);
-        yout[at] = a;
-      }
-      // every CTA of every rank read its generation before pushing, and all pushes are in: safe to advance
-      if (blockIdx.x == 0 && tid == 0) p.tp.gen[kArFusedGen] = tp_gen;
     }
   }
   pdl_launch_dependents();

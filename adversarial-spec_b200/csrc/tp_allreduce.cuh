@@ -22,19 +22,6 @@ constexpr int kArCtas = 8;
 constexpr int kArThreads = 512;
 constexpr int kArFlagBytes = 1024;
 constexpr int kArMaxRanks = 8;
-// The same exchange FUSED into the row-split GEMV (gemv_mma.cuh, EPI_TP_RESADD) keeps its own flags
-// (u32 [2 sets][tp] at byte kArFusedFlagOff of the region), its own slots (after the kernel's) and its
-// own generation / arrival counters (gen[kArFusedGen], gen[kArFusedDone]): the two mechanisms may be
-// interleaved on one stream (a short prefill between decodes) and must not share a set parity.
-constexpr int kArFusedFlagOff = 512;
-constexpr int kArFusedGen = 8;
-constexpr int kArFusedDone = 9;
-constexpr int kArGenWords = 16;
-
-// Bytes of one rank's region for `max_elems` floats per slot.
-inline size_t ar_region_bytes(int tp, int64_t max_elems) {
-  return (size_t)kArFlagBytes + (size_t)2 /*mechanisms*/ * 2 /*sets*/ * tp * (size_t)max_elems * sizeof(float);
-}
 
 struct ArParams {
   uint8_t* peer[kArMaxRanks];  // every rank's region as mapped in THIS process (peer[rank] is local)
@@ -52,28 +39,6 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-
-// Fused path helpers: slot / flag of (owner region, set, source rank)
-__device__ __forceinline__ float* ar_fused_slot(const ArParams& p, int owner, int set, int src) {
-  return reinterpret_cast<float*>(p.peer[owner] + kArFlagBytes) + (int64_t)(2 * p.tp + set * p.tp + src) * p.max_elems;
-}
-__device__ __forceinline__ unsigned int* ar_fused_flag(const ArParams& p, int owner, int set, int src) {
-  return reinterpret_cast<unsigned int*>(p.peer[owner] + kArFusedFlagOff) + set * p.tp + src;
-}
-// Bounded spin until *f == gen (latches the device watchdog instead of hanging)
-__device__ __forceinline__ void ar_wait_flag(const unsigned int* f, unsigned int gen, unsigned int site) {
-  const uint64_t t0 = global_timer_ns();
-  uint32_t spins = 0;
-  while (ld_acquire_sys(f) != gen) {
-    if ((++spins & 63u) == 0) {
-      if (*(volatile unsigned int*)&g_watchdog_code != 0) break;
-      if (global_timer_ns() - t0 > 2000000000ull) {
-        atomicCAS(&g_watchdog_code, 0u, 0x80000B00u | site);
-        break;
-      }
-    }
-  }
 }
 
 __global__ void __launch_bounds__(kArThreads) tp_allreduce_kernel(ArParams p) {
