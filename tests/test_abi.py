@@ -63,3 +63,24 @@ def test_bf16_rounding_helper_matches_torch():
     ours = weights.bf16_bits_to_f32(weights.f32_to_bf16_bits(x))
     ref = torch.from_numpy(x).bfloat16().float().numpy()
     assert (ours == ref).all()
+
+
+def test_c_example_compiles_and_links_against_the_header(tmp_path):
+    """examples/critique_panel.c is a pure-C consumer of include/advspec_engine.h: it must compile with a
+    C compiler (the header is C, not C++) and link against the built library (no GPU needed to link)."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    cc = shutil.which("gcc") or shutil.which("cc")
+    lib = root / "adversarial-spec_b200" / "libadvspec_b200.so"
+    if cc is None or not lib.exists():
+        import pytest
+        pytest.skip("needs a C compiler and the built library")
+    exe = tmp_path / "critique_panel"
+    p = subprocess.run([cc, "-std=c99", "-O2", "-Wall", "-Werror", f"-I{root / 'include'}",
+                        str(root / "examples" / "critique_panel.c"), f"-L{lib.parent}", "-ladvspec_b200",
+                        "-Wl,--allow-shlib-undefined", "-o", str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert exe.exists()
