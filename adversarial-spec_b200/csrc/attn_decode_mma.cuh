@@ -72,8 +72,19 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   auto kvz = [](int row, int chunk) { return (chunk >> 3) * HALF + row * 64 + (((chunk & 7) ^ (row & 7)) << 3); };
 
   // ---- which item am I
-  const int per_group = p.n_splits + p.opg;
-  const int grp = blockIdx.x / per_group, j = blockIdx.x % per_group;
+  // Block order: every prefix item first (group-major), then the per-opponent suffix items.  When the grid
+  // exceeds one wave (many KV heads: Phi-3, Gemma) the long prefix CTAs then all start at once and the short
+  // suffix CTAs backfill behind them, instead of a second wave that again contains full-length prefix CTAs.
+  const int n_prefix = p.Hkv * p.n_og * p.n_splits;
+  int grp, j;
+  if ((int)blockIdx.x < n_prefix) {
+    grp = blockIdx.x / p.n_splits;
+    j = blockIdx.x % p.n_splits;
+  } else {
+    const int r = blockIdx.x - n_prefix;
+    grp = r / p.opg;
+    j = p.n_splits + r % p.opg;
+  }
   const int hk = grp / p.n_og, og = grp % p.n_og;
   const int o0 = og * p.opg;
   const int n_opp = min(p.opg, p.b - o0);
