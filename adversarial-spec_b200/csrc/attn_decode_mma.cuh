@@ -1,12 +1,14 @@
 // attn_decode_mma.cuh — decode attention, second design: one kernel per layer does
 //   RoPE of the new q/k  ->  append k/v to the opponent's private suffix KV
 //   ->  split-KV flash-decoding on tensor cores (mma.sync m16n8k16, bf16)
-//   ->  log-sum-exp combine by the last split to finish (atomic ticket).
+//   ->  per-split partial (m, l, o); attn_decode_combine2_kernel (below) merges the splits.
 // A work item is (KV head, opponent group, KV source): the shared prefix is cut
 // into splits that are read ONCE for all opponents and all query heads of the KV
 // head (up to 16 query rows = one MMA M tile); each opponent's suffix is its own
-// item.  K/V tiles of 64 keys stream through a cp.async ring; the 4 warps of a
-// CTA each take 16 keys of a tile and keep a private online-softmax state.
+// item.  Prefix K/V tiles of 64 keys arrive by TMA (tensor maps over the KV region) into a
+// ring of up to six stages, suffix tiles by cp.async into the same layout; two warp groups
+// take alternate tiles, each warp 16 keys of a tile with a private online-softmax state.
+// Head dims 64 / 128 / 256 natively, 96 in the 128-wide tile with zero padding.
 // Replaces rope_decode_kernel + attn_decode_kernel + attn_decode_combine_kernel.
 #pragma once
 

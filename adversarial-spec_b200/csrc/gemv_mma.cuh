@@ -5,10 +5,11 @@
 // are the N=8 dimension of mma.sync.m16n8k16 (bf16 in, fp32 accumulate): one ldmatrix.x4
 // + one MMA per 512 bytes of W.
 //
-// One persistent CTA per SM, 288 threads.  Warp 8 is the producer: tiles of 16 rows x 1024
-// columns, one 1-D bulk async copy per row into a shared-memory ring whose rows are padded
-// by 16 bytes (conflict-free ldmatrix); the ring is primed before griddepcontrol.wait.
-// Warps 0..7 consume: warp w owns columns [w*128, w*128+128) of each tile, accumulates the
+// One persistent CTA per SM, 288 threads.  Warp 8 is the producer: tiles of 16 rows x 2048
+// columns, one 4 KB 1-D bulk async copy per row (marked L2 evict_first) into a shared-memory
+// ring whose rows are padded by 16 bytes (conflict-free ldmatrix); the ring is primed before
+// griddepcontrol.wait, and so are the constants the consumers need after it (norm weights, bias).
+// Warps 0..7 consume: warp w owns columns [w*256, w*256+256) of each tile, accumulates the
 // 16 x 8 tile of outputs over all column chunks of a row block, then the 8 warps' partials
 // are summed in shared memory and the fused epilogue (bias / residual add / gated
 // activation / fp32 store) writes the rows.  Algorithmic bytes per launch: N*K*2.
