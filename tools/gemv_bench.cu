@@ -1,4 +1,5 @@
-// Micro-benchmark of the weight-streaming GEMV variants on matrices >> L2 (build: see tools/run_gemv_bench.sh).
+// Micro-benchmark of the weight-streaming GEMV variants on matrices >> L2.
+// build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Iadversarial-spec_b200/csrc -o tools/gemv_bench tools/gemv_bench.cu
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
