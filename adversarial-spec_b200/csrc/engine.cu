@@ -949,27 +949,34 @@ void build_items(advspec_engine* e, const std::vector<int>& slots, std::vector<A
 // Decomposition of the fused decode attention for a batch: per KV head, opponents are grouped so that
 // a group's query rows (opponents x G heads) fill one 16-row MMA tile; the prefix is cut into splits
 // shared by the whole group (one CTA per SM in total), each opponent's suffix is its own CTA.
-void plan_attn2(advspec_engine* e, const std::vector<int>& slots) {
-  const auto& d = e->d;
-  const int b = (int)slots.size();
-  const int G = d.n_heads / d.n_kv_heads;
+struct Attn2Plan {
+  int opg, n_og, n_splits, ctas, n_slots;
+};
+Attn2Plan plan_attn2_shape(int b, int n_heads, int n_kv_heads, int prefix_len, int device) {
+  const int G = n_heads / n_kv_heads;
   const int opg = std::max(1, 16 / G);
   const int n_og = (b + opg - 1) / opg;
-  const int groups = d.n_kv_heads * n_og;
+  const int groups = n_kv_heads * n_og;
   // one wave of CTAs when that still cuts the prefix at least in two (GQA models); with many KV heads
   // (MHA: Phi-3 has 32) the prefix CTAs alone fill the wave and the short per-opponent suffix CTAs trail
-  const int slots_left = std::max(groups, num_sms(e->device) - b * d.n_kv_heads);
+  const int slots_left = std::max(groups, num_sms(device) - b * n_kv_heads);
   int n_splits = std::max(1, slots_left / std::max(1, groups));
   // (measured: applying this whenever it cuts the prefix finer — Gemma 9 splits instead of 6 — is slower,
   // 4.18 vs 4.08 ms/step: the trailing suffix CTAs cost more than the finer slices save)
-  if (n_splits < 2) n_splits = std::max(1, num_sms(e->device) / std::max(1, groups));
-  n_splits = std::min(n_splits, std::max(1, e->prefix_len / g_attn_min_split));
+  if (n_splits < 2) n_splits = std::max(1, num_sms(device) / std::max(1, groups));
+  n_splits = std::min(n_splits, std::max(1, prefix_len / g_attn_min_split));
   n_splits = std::min(n_splits, 300);
-  e->a2_opg = opg;
-  e->a2_n_og = n_og;
-  e->a2_n_splits = n_splits;
-  e->a2_ctas = groups * (n_splits + opg);
-  e->n_slots = n_splits + 1;
+  return Attn2Plan{opg, n_og, n_splits, groups * (n_splits + opg), n_splits + 1};
+}
+void plan_attn2(advspec_engine* e, const std::vector<int>& slots) {
+  const auto& d = e->d;
+  const int b = (int)slots.size();
+  const Attn2Plan pl = plan_attn2_shape(b, d.n_heads, d.n_kv_heads, e->prefix_len, e->device);
+  e->a2_opg = pl.opg;
+  e->a2_n_og = pl.n_og;
+  e->a2_n_splits = pl.n_splits;
+  e->a2_ctas = pl.ctas;
+  e->n_slots = pl.n_slots;
   for (int i = 0; i < 8; ++i) e->h_slots[i] = i < b ? slots[i] : 0;
 }
 
@@ -2174,6 +2181,99 @@ advspec_status advspec_op_attn_prefill(int32_t device, const void* q, int64_t ld
     return ADVSPEC_ERR_CUDA;
   }
   return op_end("op_attn_prefill");
+}
+
+advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const void* rope_cos, const void* rope_sin,
+                                      const void* prefix_k, const void* prefix_v, int64_t prefix_stride,
+                                      int32_t prefix_len, void* suffix_k, void* suffix_v, int64_t suffix_stride,
+                                      const int32_t* pos_host, void* out, int32_t b, int32_t n_heads,
+                                      int32_t n_kv_heads, int32_t head_dim) {
+  advspec_status s = op_begin(device);
+  if (s) return s;
+  const int G = n_kv_heads > 0 ? n_heads / n_kv_heads : 0;
+  if (b < 1 || b > 8 || n_kv_heads < 1 || n_heads % n_kv_heads || G > 16 || n_heads > 255 || !pos_host ||
+      (head_dim != 64 && head_dim != 96 && head_dim != 128 && head_dim != 256) || prefix_len < 1 ||
+      prefix_len > prefix_stride) {
+    g_create_error = "op_attn_decode: need 1 <= b <= 8, heads/kv_heads <= 16, head_dim in {64,96,128,256}, "
+                     "1 <= prefix_len <= prefix_stride";
+    return ADVSPEC_ERR_INVALID;
+  }
+  for (int i = 0; i < b; ++i)
+    if (pos_host[i] < prefix_len || pos_host[i] - prefix_len >= suffix_stride) {
+      g_create_error = "op_attn_decode: pos[i] must be prefix_len + (suffix tokens already stored) < suffix capacity";
+      return ADVSPEC_ERR_INVALID;
+    }
+  if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
+  const Attn2Plan pl = plan_attn2_shape(b, n_heads, n_kv_heads, prefix_len, device);
+  CUtensorMap hm[2];
+  const int64_t rows = (int64_t)n_kv_heads * prefix_stride;
+  if (!make_tmap(&hm[0], prefix_k, rows, head_dim, head_dim, 64) ||
+      !make_tmap(&hm[1], prefix_v, rows, head_dim, head_dim, 64)) {
+    g_create_error = "op_attn_decode: cuTensorMapEncodeTiled failed";
+    return ADVSPEC_ERR_CUDA;
+  }
+  CUtensorMap* dmaps = nullptr;
+  int* dpos = nullptr;
+  float *pm = nullptr, *plv = nullptr, *po = nullptr;
+  const size_t nrow = (size_t)b * n_heads * pl.n_slots;
+  auto cleanup = [&]() {
+    cudaFree(dmaps);
+    cudaFree(dpos);
+    cudaFree(pm);
+    cudaFree(plv);
+    cudaFree(po);
+  };
+  if (cudaMalloc(reinterpret_cast<void**>(&dmaps), sizeof hm) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&dpos), 8 * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&pm), nrow * 4) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&plv), nrow * 4) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&po), nrow * head_dim * 4) != cudaSuccess) {
+    cleanup();
+    g_create_error = "op_attn_decode: out of device memory";
+    return ADVSPEC_ERR_OOM;
+  }
+  cudaMemcpy(dmaps, hm, sizeof hm, cudaMemcpyHostToDevice);
+  cudaMemcpy(dpos, pos_host, b * sizeof(int), cudaMemcpyHostToDevice);
+  AttnDecode2Params a2{};
+  a2.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  a2.rope_cos = reinterpret_cast<const float*>(rope_cos);
+  a2.rope_sin = reinterpret_cast<const float*>(rope_sin);
+  a2.pk = reinterpret_cast<const __nv_bfloat16*>(prefix_k);
+  a2.pv = reinterpret_cast<const __nv_bfloat16*>(prefix_v);
+  a2.pstride = prefix_stride;
+  a2.sk = reinterpret_cast<__nv_bfloat16*>(suffix_k);
+  a2.sv = reinterpret_cast<__nv_bfloat16*>(suffix_v);
+  a2.sstride = suffix_stride;
+  a2.maps = dmaps;
+  a2.pos_b = dpos;
+  for (int i = 0; i < 8; ++i) a2.slots[i] = i < b ? i : 0;
+  a2.prefix_len = prefix_len;
+  a2.part_m = pm;
+  a2.part_l = plv;
+  a2.part_o = po;
+  a2.b = b;
+  a2.H = n_heads;
+  a2.Hkv = n_kv_heads;
+  a2.G = G;
+  a2.opg = pl.opg;
+  a2.n_og = pl.n_og;
+  a2.n_splits = pl.n_splits;
+  a2.n_slots = pl.n_slots;
+  a2.scale = 1.0f / sqrtf((float)head_dim);
+  a2.dh = head_dim;
+  cudaError_t r = launch_attn_decode2(a2, pl.ctas, head_dim, 0, false);
+  if (r == cudaSuccess)
+    r = launch_pdl(attn_decode_combine2_kernel, dim3(b * n_heads), dim3(128), 0, (cudaStream_t)0, false,
+                   (const float*)pm, (const float*)plv, (const float*)po, reinterpret_cast<__nv_bfloat16*>(out),
+                   pl.n_slots, (int)head_dim);
+  if (r != cudaSuccess) {
+    cleanup();
+    g_create_error = std::string("op_attn_decode launch: ") + cudaGetErrorString(r);
+    return ADVSPEC_ERR_CUDA;
+  }
+  s = op_end("op_attn_decode");
+  cleanup();
+  return s;
 }
 
 }  // extern "C"

@@ -81,7 +81,7 @@ EXPORTED_SYMBOLS = [
     "advspec_release_seqs", "advspec_release_prefix", "advspec_prefix_kv_region",
     "advspec_prefix_adopt", "advspec_get_timing", "advspec_profile_decode_step",
     "advspec_decode_step_bytes", "advspec_ktrace_enable", "advspec_ktrace_read", "advspec_ktrace_phases", "advspec_op_gemm", "advspec_op_gemm_check", "advspec_op_gemv",
-    "advspec_op_attn_prefill",
+    "advspec_op_attn_prefill", "advspec_op_attn_decode",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -132,6 +132,8 @@ def load_library() -> C.CDLL:
         "advspec_op_gemm_check": (i32, [i32, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32]),
         "advspec_op_gemv": (i32, [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32]),
         "advspec_op_attn_prefill": (i32, [i32, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32]),
+        "advspec_op_attn_decode": (i32, [i32, vp, vp, vp, vp, vp, i64, i32, vp, vp, i64, P(i32), vp, i32, i32,
+                                         i32, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = header/library drift

@@ -100,6 +100,7 @@ REGISTRY: dict[str, ModelSpec] = {
         _llama("tiny-qwen2", 2, 256, 4, 2, 512, 1024, head_dim=64, family="qwen2", qkv_bias=True,
                theta=1000000.0, eps=1e-6),
         _llama("tiny-gqa4", 2, 512, 8, 2, 768, 1024, head_dim=64),
+        _llama("tiny-mistral", 2, 512, 8, 2, 1024, 2048, head_dim=64, family="mistral", theta=10000.0),
         _llama("tiny-phi3", 2, 192, 2, 2, 512, 1024, head_dim=96, family="phi3", theta=10000.0),
         _llama("tiny-gemma256", 2, 512, 2, 2, 512, 1024, head_dim=256, family="gemma", act=1,
                tied_lm_head=True, embed_scale=math.sqrt(512.0), theta=10000.0, eps=1e-6),
@@ -107,6 +108,9 @@ REGISTRY: dict[str, ModelSpec] = {
                tied_lm_head=True, embed_scale=16.0, theta=10000.0, eps=1e-6),
         # Llama-3-8B layer shape with 2 layers: the CPU-baseline sample (per-layer cost scales to 32)
         _llama("llama-3-8b-2layer", 2, 4096, 32, 8, 14336, 128256),
+        # Llama-3-70B's layer shape (d 8192, 64/8 heads, MLP 28672), 2 layers, a 32K vocabulary: the
+        # tensor-parallel parity case a CPU oracle can hold (the lm_head is not what TP=8 is about)
+        _llama("llama-3-70b-2layer-v32k", 2, 8192, 64, 8, 28672, 32768),
     ]
 }
 

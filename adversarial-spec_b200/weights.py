@@ -93,8 +93,20 @@ class BlobWriter:
         self.layout = blob_layout(spec, embed_rows)
         self.buf = np.zeros(self.layout.total, dtype=np.uint8)
 
-    def put(self, layer: int, name: str, value: np.ndarray) -> None:
+    def put(self, layer: int, name: str, value) -> None:
+        """`value`: a numpy array, or a torch tensor (bf16 matrices then convert through torch's
+        multi-threaded round-to-nearest-even cast — same bits, much faster for full-width models)."""
         off, shape, kind = self.layout.offsets[(layer, name)]
+        if kind == "bf16" and hasattr(value, "bfloat16"):
+            if tuple(value.shape) != shape:
+                raise ValueError(f"{name}[{layer}]: shape {tuple(value.shape)}, expected {shape}")
+            import torch
+
+            raw = value.detach().contiguous().bfloat16().view(torch.int16).numpy().reshape(-1).view(np.uint8)
+            self.buf[off: off + raw.size] = raw
+            return
+        if hasattr(value, "detach"):
+            value = value.detach().float().numpy()
         v = np.asarray(value, dtype=np.float32)
         if tuple(v.shape) != shape:
             raise ValueError(f"{name}[{layer}]: shape {v.shape}, expected {shape}")

@@ -269,6 +269,23 @@ advspec_status advspec_op_attn_prefill(int32_t device, const void *q,
                                        int32_t n_heads, int32_t n_kv_heads,
                                        int32_t head_dim, int32_t impl);
 
+/* One decode-attention step, the engine's kernels on caller-supplied device buffers (tests/ compare it
+ * with an fp32 reference).  qkv: bf16 [b][(n_heads+2*n_kv_heads)*head_dim] raw projections of each
+ * opponent's new token; rope_cos/rope_sin: f32 [>= max pos+1][head_dim/2]; prefix K/V: bf16
+ * [n_kv_heads][prefix_stride][head_dim] of which prefix_len tokens are valid, shared by all opponents;
+ * suffix K/V: bf16 [b][n_kv_heads][suffix_stride][head_dim], opponent i holding pos[i]-prefix_len tokens
+ * already (RoPE applied); pos: HOST int32 [b], absolute position of each new token.  The kernel rotates
+ * q and k, appends k/v at suffix row pos[i]-prefix_len (side effect, as in the engine) and writes
+ * out: bf16 [b][n_heads*head_dim] = softmax(q k^T / sqrt(head_dim)) v over prefix + suffix + new token. */
+advspec_status advspec_op_attn_decode(int32_t device, const void *qkv,
+                                      const void *rope_cos, const void *rope_sin,
+                                      const void *prefix_k, const void *prefix_v,
+                                      int64_t prefix_stride, int32_t prefix_len,
+                                      void *suffix_k, void *suffix_v,
+                                      int64_t suffix_stride, const int32_t *pos,
+                                      void *out, int32_t b, int32_t n_heads,
+                                      int32_t n_kv_heads, int32_t head_dim);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,7 @@ import advspec_loader
 
 advspec_loader.load()
 from advspec_b200.model_spec import ModelSpec  # noqa: E402
-from advspec_b200.weights import BlobWriter, interleave_gate_up  # noqa: E402
+from advspec_b200.weights import BlobWriter  # noqa: E402
 
 
 def hf_config(spec: ModelSpec):
@@ -82,13 +82,46 @@ def build_hf_model(spec: ModelSpec, seed: int):
     return model
 
 
+def build_hf_model_fast(spec: ModelSpec, seed: int, std: float = 0.02):
+    """Same contract as build_hf_model for FULL-WIDTH shapes (billions of parameters): HF's own
+    per-module initialisation is skipped and every matrix is drawn N(0, std) in one pass, then rounded
+    to bf16 once (so the engine's blob holds exactly the oracle's values).  The forward is still
+    transformers' own modeling code; only the weight VALUES differ from build_hf_model's."""
+    import transformers as tf
+    from transformers.initialization import no_init_weights
+
+    cfg = hf_config(spec)
+    with no_init_weights():
+        model = tf.AutoModelForCausalLM.from_config(cfg, attn_implementation="eager").float().eval()
+    g = torch.Generator().manual_seed(seed)
+    chunk = 32 * 1024 * 1024  # draw and round through reused scratch buffers: no 6 GB temporaries
+    scr, scb = torch.empty(chunk), torch.empty(chunk, dtype=torch.bfloat16)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 1:
+                base = 0.0 if (name.endswith("bias") or spec.family == "gemma") else 1.0
+                p.copy_(base + 0.1 * torch.randn(p.shape, generator=g))
+                if name.endswith("bias"):
+                    p.mul_(0.2)
+            else:
+                flat = p.view(-1)
+                for o in range(0, flat.numel(), chunk):
+                    n = min(chunk, flat.numel() - o)
+                    scr[:n].normal_(0.0, std, generator=g)
+                    scb[:n].copy_(scr[:n])
+                    flat[o:o + n].copy_(scb[:n])
+        if spec.tied_lm_head:
+            model.tie_weights()
+    return model
+
+
 def rope_inv_freq(model) -> np.ndarray:
     return model.model.rotary_emb.inv_freq.detach().float().numpy().copy()
 
 
 def export_blob(spec: ModelSpec, model) -> np.ndarray:
     """HF state dict -> the engine's weight blob (uint8 array)."""
-    sd = {k: v.detach().float().numpy() for k, v in model.state_dict().items()}
+    sd = {k: v.detach().float() for k, v in model.state_dict().items()}
     w = BlobWriter(spec)
     w.put(-1, "embed", sd["model.embed_tokens.weight"])
     gemma = spec.family == "gemma"
@@ -100,16 +133,17 @@ def export_blob(spec: ModelSpec, model) -> np.ndarray:
             gu = sd[p + "mlp.gate_up_proj.weight"]
             gate, up = gu[: spec.d_ff], gu[spec.d_ff:]
         else:
-            qkv = np.concatenate([sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"],
-                                  sd[p + "self_attn.v_proj.weight"]], axis=0)
+            qkv = torch.cat([sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"],
+                             sd[p + "self_attn.v_proj.weight"]], dim=0)
             gate, up = sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]
         w.put(l, "wqkv", qkv)
         if spec.qkv_bias:
-            w.put(l, "bqkv", np.concatenate([sd[p + "self_attn.q_proj.bias"], sd[p + "self_attn.k_proj.bias"],
-                                             sd[p + "self_attn.v_proj.bias"]]))
+            w.put(l, "bqkv", torch.cat([sd[p + "self_attn.q_proj.bias"], sd[p + "self_attn.k_proj.bias"],
+                                        sd[p + "self_attn.v_proj.bias"]]))
         w.put(l, "wo", sd[p + "self_attn.o_proj.weight"])
         w.put(l, "mlp_norm", sd[p + "post_attention_layernorm.weight"] + (1.0 if gemma else 0.0))
-        w.put(l, "wgu", interleave_gate_up(gate, up))
+        # rows (gate_0, up_0, gate_1, up_1, ...): weights.interleave_gate_up, on torch tensors
+        w.put(l, "wgu", torch.stack([gate, up], dim=1).reshape(2 * spec.d_ff, spec.d_model))
         w.put(l, "wd", sd[p + "mlp.down_proj.weight"])
     w.put(-1, "final_norm", sd["model.norm.weight"] + (1.0 if gemma else 0.0))
     if not spec.tied_lm_head:
@@ -122,6 +156,21 @@ def hf_logits(model, tokens) -> np.ndarray:
     """fp32 logits [n_tokens, vocab] for one sequence."""
     ids = torch.tensor([list(tokens)], dtype=torch.long)
     return model(input_ids=ids, use_cache=False).logits[0].float().numpy()
+
+
+@torch.no_grad()
+def hf_logits_last(model, tokens, keep: int, attn: str = "sdpa") -> np.ndarray:
+    """fp32 logits of the LAST `keep` positions only ([keep, vocab]) — full-width vocabularies make
+    all-position logits (n x 128K floats) pointless.  `attn="sdpa"` keeps the S x S score matrix out of
+    memory for 5K-9K-token prompts (same fp32 math as the eager path; torch's CPU kernel)."""
+    ids = torch.tensor([list(tokens)], dtype=torch.long)
+    prev = model.config._attn_implementation
+    model.config._attn_implementation = attn
+    try:
+        out = model(input_ids=ids, use_cache=False, logits_to_keep=keep).logits[0].float().numpy()
+    finally:
+        model.config._attn_implementation = prev
+    return out
 
 
 @torch.no_grad()

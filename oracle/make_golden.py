@@ -212,7 +212,11 @@ def make_message_fixtures() -> None:
     print(f"reference_messages.json: {len(rows)} rows")
 
 
-def make_hf_logits() -> None:
+HF_GOLDEN_NAMES = ["tiny-llama", "tiny-llama-128", "tiny-qwen2", "tiny-gemma", "tiny-phi3", "tiny-gemma256",
+                   "tiny-mistral"]
+
+
+def make_hf_logits(only=None) -> None:
     import numpy as np
 
     import advspec_loader
@@ -223,7 +227,7 @@ def make_hf_logits() -> None:
 
     import transformers
 
-    for name in ["tiny-llama", "tiny-llama-128", "tiny-qwen2", "tiny-gemma", "tiny-phi3", "tiny-gemma256"]:
+    for name in (only or HF_GOLDEN_NAMES):
         spec = model_spec.resolve(name)
         model = hf_oracle.build_hf_model(spec, 1234)
         toks = np.random.default_rng(7).integers(0, spec.vocab_size, 24)
@@ -241,6 +245,9 @@ def make_hf_logits() -> None:
 
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
+    if len(sys.argv) > 2 and sys.argv[1] == "--hf-only":  # add a model's logits without touching the rest
+        make_hf_logits(sys.argv[2:])
+        sys.exit(0)
     if REF_SCRIPTS.exists():
         make_reference_cases()
         make_reference_flows()

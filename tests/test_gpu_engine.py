@@ -8,7 +8,7 @@ from tests.gpu_util import TOL_MAX, TOL_RMS, make_engine, rel_errors
 
 pytestmark = pytest.mark.gpu
 
-MODELS = ["tiny-llama", "tiny-llama-128", "tiny-qwen2", "tiny-gemma", "tiny-phi3", "tiny-gemma256"]
+MODELS = ["tiny-llama", "tiny-llama-128", "tiny-qwen2", "tiny-gemma", "tiny-phi3", "tiny-gemma256", "tiny-mistral"]
 
 
 def _tokens(spec, n, seed):

@@ -146,3 +146,86 @@ def test_attn_prefill(cuda_device, diag, cfg, impl):
     diag[f"attn_prefill/{cfg}/impl{impl}"] = e
     # outputs are O(1); bf16 output rounding + bf16 P in the tensor-core kernel
     assert e < 3e-2, e
+
+
+def _rope(x, cos, sin):
+    """rotate_half RoPE on [..., Dh] with per-row cos/sin [..., Dh/2] (fp32)."""
+    half = x.shape[-1] // 2
+    a, b = x[..., :half], x[..., half:]
+    return torch.cat([a * cos - b * sin, b * cos + a * sin], dim=-1)
+
+
+# (prefix_len, b, H, Hkv, Dh, suffix lengths already stored per opponent): the benchmark's own
+# configuration first (5,068-token prefix, 3 opponents, Llama-3-8B heads), then Qwen2 (G = 7: two
+# opponent groups per KV head at b = 3), Phi-3 (MHA, head_dim 96 in the padded 128-wide tile), Gemma
+# (MHA, head_dim 256), the full batch, a tensor-parallel rank's share of Llama-3-70B (one KV head, G = 8),
+# and suffix lengths around the 64-key tile boundary.
+ATTN_DECODE_CASES = [
+    (5068, 3, 32, 8, 128, [0, 5, 17]),
+    (5068, 3, 32, 8, 128, [63, 64, 65]),
+    (5068, 8, 32, 8, 128, [1, 63, 64, 65, 0, 130, 200, 255]),
+    (5068, 1, 32, 8, 128, [255]),
+    (2100, 3, 28, 4, 128, [3, 64, 100]),
+    (2100, 3, 32, 32, 96, [1, 63, 65]),
+    (2100, 8, 32, 32, 96, [0, 1, 2, 3, 64, 65, 66, 127]),
+    (2100, 3, 16, 16, 256, [0, 64, 129]),
+    (9000, 1, 8, 1, 128, [31]),
+    (300, 2, 4, 2, 64, [0, 70]),
+    (100, 3, 8, 2, 128, [5, 5, 5]),
+]
+
+
+@pytest.mark.parametrize("case", ATTN_DECODE_CASES)
+def test_attn_decode_op(cuda_device, diag, case):
+    """advspec_op_attn_decode (RoPE of the new q/k, KV append, split-KV attention over the shared prefix and
+    each opponent's suffix, merge) against an fp32 torch reference at the engine's production shapes."""
+    prefix_len, b, H, Hkv, Dh, suf = case
+    lib = eng.load_library()
+    g = torch.Generator(device="cuda").manual_seed(prefix_len + 31 * b + H + Dh)
+    pstride, sstride = prefix_len + 91, 320
+    half = Dh // 2
+    QKV = (H + 2 * Hkv) * Dh
+    qkv = torch.randn(b, QKV, device="cuda", generator=g).bfloat16()
+    pk = torch.randn(Hkv, pstride, Dh, device="cuda", generator=g).bfloat16()
+    pv = torch.randn(Hkv, pstride, Dh, device="cuda", generator=g).bfloat16()
+    pk[:, prefix_len:] = 0  # rows the engine never wrote hold zeros (TMA loads whole 64-key boxes)
+    pv[:, prefix_len:] = 0
+    sk = torch.zeros(b, Hkv, sstride, Dh, device="cuda", dtype=torch.bfloat16)
+    sv = torch.zeros_like(sk)
+    for i, t in enumerate(suf):
+        sk[i, :, :t] = torch.randn(Hkv, t, Dh, device="cuda", generator=g).bfloat16()
+        sv[i, :, :t] = torch.randn(Hkv, t, Dh, device="cuda", generator=g).bfloat16()
+    max_pos = prefix_len + sstride
+    inv = 1.0 / (10000.0 ** (torch.arange(0, Dh, 2, device="cuda").float() / Dh))
+    ang = torch.arange(max_pos, device="cuda").float()[:, None] * inv[None, :]
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    pos = np.asarray([prefix_len + t for t in suf], dtype=np.int32)
+    out = torch.zeros(b, H * Dh, device="cuda", dtype=torch.bfloat16)
+    sk_before, sv_before = sk.clone(), sv.clone()
+
+    st = lib.advspec_op_attn_decode(0, _ptr(qkv), _ptr(cos), _ptr(sin), _ptr(pk), _ptr(pv), pstride, prefix_len,
+                                    _ptr(sk), _ptr(sv), sstride, pos.ctypes.data_as(C.POINTER(C.c_int32)),
+                                    _ptr(out), b, H, Hkv, Dh)
+    assert st == 0, _err(lib)
+
+    worst, worst_k = 0.0, 0.0
+    for i, t in enumerate(suf):
+        c, s = cos[prefix_len + t], sin[prefix_len + t]
+        q = _rope(qkv[i, : H * Dh].float().reshape(H, Dh), c, s).bfloat16().float()
+        knew = _rope(qkv[i, H * Dh: (H + Hkv) * Dh].float().reshape(Hkv, Dh), c, s).bfloat16()
+        vnew = qkv[i, (H + Hkv) * Dh:].reshape(Hkv, Dh)
+        # side effect: the new k (rotated) and v rows are appended at suffix row t, nothing else changes
+        worst_k = max(worst_k, float((sk[i, :, t].float() - knew.float()).abs().max()))
+        assert torch.equal(sv[i, :, t], vnew)
+        assert torch.equal(sk[i, :, :t], sk_before[i, :, :t]) and torch.equal(sv[i, :, :t], sv_before[i, :, :t])
+        k = torch.cat([pk[:, :prefix_len], sk_before[i, :, :t], knew[:, None]], dim=1).float()
+        v = torch.cat([pv[:, :prefix_len], sv_before[i, :, :t], vnew[:, None]], dim=1).float()
+        k = k.repeat_interleave(H // Hkv, dim=0)
+        v = v.repeat_interleave(H // Hkv, dim=0)
+        sc = torch.einsum("hd,hkd->hk", q, k) / (Dh ** 0.5)
+        ref = torch.einsum("hk,hkd->hd", sc.softmax(-1), v).reshape(H * Dh)
+        worst = max(worst, float((out[i].float() - ref).abs().max()))
+    diag[f"attn_decode_op/{case}"] = {"max_abs": worst, "k_append_max_abs": worst_k}
+    # outputs are averages of N(0,1) values over thousands of keys (|o| ~ 0.05-1); bf16 P and bf16 output
+    assert worst_k < 2e-2, worst_k
+    assert worst < 1e-2, worst

@@ -11,7 +11,7 @@ from advspec_b200 import model_spec
 from oracle import hf_oracle, restate, sampling_ref
 
 GOLDEN = Path(__file__).parent / "golden"
-NAMES = ["tiny-llama", "tiny-llama-128", "tiny-qwen2", "tiny-gemma", "tiny-phi3", "tiny-gemma256"]
+NAMES = ["tiny-llama", "tiny-llama-128", "tiny-qwen2", "tiny-gemma", "tiny-phi3", "tiny-gemma256", "tiny-mistral"]
 
 
 @pytest.fixture(scope="module", params=NAMES)

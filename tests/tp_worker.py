@@ -27,7 +27,8 @@ def main():
     for name in [m for m in os.environ.get("TP_MODELS", "tiny-gqa4,tiny-llama-128").split(",") if m]:
         from oracle import hf_oracle  # the checker (test infrastructure)
         spec = model_spec.resolve(name)
-        model = hf_oracle.build_hf_model(spec, 11)
+        big = spec.n_params() > 200_000_000  # full-width shapes: one-pass init instead of HF's per-module init
+        model = hf_oracle.build_hf_model_fast(spec, 11) if big else hf_oracle.build_hf_model(spec, 11)
         full = hf_oracle.export_blob(spec, model)
         rng = np.random.default_rng(5)
         prompt = rng.integers(0, spec.vocab_size, 200).tolist()
