@@ -5,8 +5,8 @@ Only the fields the reference reads exist on the response:
 ``.choices[0].message.content`` and ``.usage.prompt_tokens/.completion_tokens``
 (models.py:629, 639-640).  The reference enters this function from N threads at
 once with identical ``messages`` when opponents share a model (models.py:699);
-those calls are coalesced here — the first caller waits a few milliseconds for
-its siblings, then ONE prefill serves them all.  Callers that can see the whole
+those calls are coalesced here — the first caller waits until arrivals go quiet (2 ms
+without a new sibling, 25 ms at most), then ONE prefill serves them all.  Callers that can see the whole
 panel should use ``models.call_models_parallel`` (seam B2) instead.
 """
 
@@ -65,6 +65,7 @@ class _Batch:
         self.closed = False
         self.results: Optional[list] = None
         self.done = threading.Event()
+        self.arrived = threading.Condition()
 
 
 _pending: dict[tuple, _Batch] = {}
@@ -72,11 +73,33 @@ _pending_mu = threading.Lock()
 _call_counter = 0
 
 
-def _coalesce_window_s() -> float:
+def _env_ms(name: str, default: float) -> float:
     try:
-        return float(os.environ.get("ADVSPEC_COALESCE_MS", "25")) / 1000.0
+        return float(os.environ.get(name, default)) / 1000.0
     except ValueError:
-        return 0.025
+        return default / 1000.0
+
+
+def _gather_siblings(b: "_Batch") -> None:
+    """The leader's wait for the sibling calls of one fan-out.  The reference starts its N threads within
+    microseconds of each other (models.py:699-719), so the leader does not sit out a fixed window: it
+    returns as soon as no new caller has joined for ADVSPEC_COALESCE_QUIET_MS (default 2 ms), and never
+    waits longer than ADVSPEC_COALESCE_MS (default 25 ms) in total."""
+    deadline = time.perf_counter() + _env_ms("ADVSPEC_COALESCE_MS", 25.0)
+    quiet = _env_ms("ADVSPEC_COALESCE_QUIET_MS", 2.0)
+    seen, last_change = b.n, time.perf_counter()
+    while True:
+        now = time.perf_counter()
+        if now >= deadline:
+            return
+        with b.arrived:
+            b.arrived.wait(timeout=min(quiet, deadline - now))
+            n = b.n
+        now = time.perf_counter()
+        if n != seen:
+            seen, last_change = n, now
+        elif now - last_change >= quiet:
+            return
 
 
 def completion(*, model: str, messages: list[dict], max_tokens: int = 8000, timeout: Any = None,
@@ -107,8 +130,11 @@ def completion(*, model: str, messages: list[dict], max_tokens: int = 8000, time
         b.n += 1
         base = _call_counter
         _call_counter += 1
+    if not leader:
+        with b.arrived:
+            b.arrived.notify_all()
     if leader:
-        time.sleep(_coalesce_window_s())
+        _gather_siblings(b)
         with _pending_mu:
             b.closed = True
             if _pending.get(key) is b:

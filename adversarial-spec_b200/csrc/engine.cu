@@ -1629,14 +1629,17 @@ advspec_status advspec_set_rope_inv_freq(advspec_engine* e, const float* inv_fre
   return ADVSPEC_OK;
 }
 
-static advspec_status prefill_impl(advspec_engine* e, const int32_t* tokens, int32_t n, float* all_logits_host) {
+// Prefill `n` tokens at positions pos_base.. against the KV of positions 0..pos_base-1 already in the
+// prefix region (pos_base = 0: a fresh prompt).
+static advspec_status prefill_impl(advspec_engine* e, const int32_t* tokens, int32_t n, float* all_logits_host,
+                                   int32_t pos_base = 0) {
   const auto& d = e->d;
   if (!e->weights_ready) {
     e->fail("weights not loaded");
     return ADVSPEC_ERR_STATE;
   }
-  if (!tokens || n < 1 || n > d.max_prefix_tokens) {
-    e->fail("prompt of %d tokens outside 1..%d", n, d.max_prefix_tokens);
+  if (!tokens || n < 1 || pos_base < 0 || (int64_t)pos_base + n > d.max_prefix_tokens) {
+    e->fail("prompt of %d tokens at position %d outside 1..%d", n, pos_base, d.max_prefix_tokens);
     return ADVSPEC_ERR_INVALID;
   }
   for (int i = 0; i < n; ++i)
@@ -1667,7 +1670,7 @@ static advspec_status prefill_impl(advspec_engine* e, const int32_t* tokens, int
       st = ADVSPEC_ERR_CUDA;
       break;
     }
-    st = prefill_chunk(e, m, c0);
+    st = prefill_chunk(e, m, pos_base + c0);
     if (st != ADVSPEC_OK) break;
     if (all_logits_dev) {
       rmsnorm_kernel<<<m, 256, 0, e->stream>>>(e->p_x, final_norm_w(e), e->p_xn, d.d_model, d.norm_eps);
@@ -1720,6 +1723,38 @@ advspec_status advspec_prefill(advspec_engine* e, const int32_t* tokens, int32_t
   e->prefix_len = n_tokens;
   e->logits_broadcast = true;
   *prefix_id = e->prefix_gen;
+  return ADVSPEC_OK;
+}
+
+advspec_status advspec_prefill_extend(advspec_engine* e, int32_t prefix_id, int32_t keep_tokens,
+                                      const int32_t* tokens, int32_t n_tokens, int32_t* new_prefix_id) {
+  if (!e || !new_prefix_id) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->prefix_gen == 0 || prefix_id != e->prefix_gen) {
+    e->fail("prefix %d is not live", prefix_id);
+    return ADVSPEC_ERR_STATE;
+  }
+  if (keep_tokens < 0 || keep_tokens > e->prefix_len || n_tokens < 0 ||
+      (n_tokens == 0 && keep_tokens != e->prefix_len) || (keep_tokens == 0 && n_tokens == 0)) {
+    e->fail("prefill_extend: keep %d of a %d-token prefix with %d new tokens is not valid (keep the whole "
+            "prefix to re-arm it, or append at least one token)", keep_tokens, e->prefix_len, n_tokens);
+    return ADVSPEC_ERR_INVALID;
+  }
+  const int old_gen = e->prefix_gen;
+  if (n_tokens > 0) {
+    // the first keep_tokens rows of the prefix KV stay; rows past them are overwritten by the new tail
+    advspec_status st = prefill_impl(e, tokens, n_tokens, nullptr, keep_tokens);
+    if (st != ADVSPEC_OK) return st;  // (prefill_impl dropped the live prefix: a failed tail leaves none)
+  } else {
+    e->tm.prefill_ms = 0.f;
+    for (bool& u : e->slot_used) u = false;
+  }
+  (void)old_gen;
+  static int next_gen = 1 << 24;
+  e->prefix_gen = next_gen++;
+  e->prefix_len = keep_tokens + n_tokens;
+  e->logits_broadcast = true;
+  *new_prefix_id = e->prefix_gen;
   return ADVSPEC_OK;
 }
 

@@ -111,6 +111,21 @@ def validate_models_before_run(models: list[str], bedrock_mode: bool) -> None:
         sys.exit(2)
 
 
+def read_spec_from_stdin() -> str:
+    """stdin, stripped (reference debate.py:778).  Under torchrun with ADVSPEC_TP=k the k ranks inherit ONE
+    stdin, so only rank 0 reads it and the text is broadcast to the other ranks of the tensor-parallel group
+    (every rank must run the identical round)."""
+    try:
+        tp = int(os.environ.get("ADVSPEC_TP", "1"))
+    except ValueError:
+        tp = 1
+    if tp <= 1:
+        return sys.stdin.read().strip()
+    rank = int(os.environ.get("RANK", "0"))
+    text = sys.stdin.read().strip() if rank == 0 else None
+    return _models.runtime.broadcast_object(text, src=0)
+
+
 def load_or_resume_session(args: argparse.Namespace, models: list[str]):
     session_state = None
     if args.resume:
@@ -128,7 +143,7 @@ def load_or_resume_session(args: argparse.Namespace, models: list[str]):
         args.preserve_intent = session_state.preserve_intent or args.preserve_intent
         models = session_state.models
     else:
-        spec = sys.stdin.read().strip()
+        spec = read_spec_from_stdin()
         if not spec:
             print("Error: No spec provided via stdin", file=sys.stderr)
             sys.exit(1)
@@ -218,7 +233,7 @@ def output_results(args, results, models: list[str], all_agreed: bool, user_feed
 def handle_export_tasks(args, models: list[str]) -> None:
     """`export-tasks`: the other `completion` call site (reference debate.py:688-736) — one model, one user
     message, max_tokens 8000, temperature 0.3, no retry; a local b200/ model runs on the same engine."""
-    spec = sys.stdin.read().strip()
+    spec = read_spec_from_stdin()
     if not spec:
         print("Error: No spec provided via stdin", file=sys.stderr)
         sys.exit(1)
@@ -253,13 +268,40 @@ def _tensor_parallel_follower() -> bool:
         return False
 
 
-def main() -> None:
+def _forward_to_server(args) -> bool:
+    """ADVSPEC_SERVER=<unix socket>: run this invocation in the resident server process (resident.py) so the
+    engines it loaded for earlier rounds are reused; stdout, stderr and the exit code come back unchanged."""
+    path = os.environ.get("ADVSPEC_SERVER")
+    if not path or args.action not in ("critique", "export-tasks"):
+        return False
+    if __package__ in (None, ""):
+        from advspec_b200 import resident
+    else:
+        from . import resident
+    needs_stdin = not (args.action == "critique" and args.resume)
+    stdin_text = sys.stdin.read() if needs_stdin else ""
+    try:
+        r = resident.request(path, sys.argv[1:], stdin_text)
+    except OSError as e:
+        print(f"Error: ADVSPEC_SERVER={path} is set but no server answers there ({e}); start one with "
+              f"`python adversarial-spec_b200/resident.py serve --socket {path}` or unset ADVSPEC_SERVER",
+              file=sys.stderr)
+        sys.exit(2)
+    sys.stdout.write(r.get("stdout", ""))
+    sys.stderr.write(r.get("stderr", ""))
+    sys.stdout.flush()
+    sys.exit(int(r.get("code", 1)))
+
+
+def main(_forward: bool = True) -> None:
     if _tensor_parallel_follower():
         sink = open(os.devnull, "w")
         sys.stdout = sys.stderr = sink
         _session.SessionState.save = lambda self: None
         globals()["save_checkpoint"] = lambda *a, **k: None
     args = create_parser().parse_args()
+    if _forward and _forward_to_server(args):
+        return
     if args.action == "providers":
         _providers.list_providers()
         return

@@ -76,7 +76,7 @@ EXPORTED_SYMBOLS = [
     "advspec_engine_destroy", "advspec_last_error", "advspec_tp_unique_id", "advspec_tp_init",
     "advspec_tp_ipc_export", "advspec_tp_ipc_import",
     "advspec_load_weights",
-    "advspec_init_weights_random", "advspec_set_rope_inv_freq", "advspec_prefill", "advspec_fork",
+    "advspec_init_weights_random", "advspec_set_rope_inv_freq", "advspec_prefill", "advspec_prefill_extend", "advspec_fork",
     "advspec_decode", "advspec_decode_step", "advspec_get_logits", "advspec_prefill_logits",
     "advspec_release_seqs", "advspec_release_prefix", "advspec_prefix_kv_region",
     "advspec_prefix_adopt", "advspec_get_timing", "advspec_profile_decode_step",
@@ -113,6 +113,7 @@ def load_library() -> C.CDLL:
         "advspec_init_weights_random": (i32, [vp, C.c_uint64, f32]),
         "advspec_set_rope_inv_freq": (i32, [vp, P(f32), i32]),
         "advspec_prefill": (i32, [vp, P(i32), i32, P(i32)]),
+        "advspec_prefill_extend": (i32, [vp, i32, i32, P(i32), i32, P(i32)]),
         "advspec_fork": (i32, [vp, i32, i32, P(C.c_uint64), P(i32)]),
         "advspec_decode": (i32, [vp, P(i32), i32, i32, f32, i32, P(i32), P(i32)]),
         "advspec_decode_step": (i32, [vp, P(i32), i32, P(i32)]),
@@ -252,6 +253,14 @@ class Engine:
         t = _i32(tokens)
         pid = C.c_int32()
         self._check(self.lib.advspec_prefill(self.h, _p(t, C.c_int32), t.size, C.byref(pid)))
+        return pid.value
+
+    def prefill_extend(self, prefix_id: int, keep_tokens: int, tail: Sequence[int]) -> int:
+        """Keep the first `keep_tokens` tokens' KV of a live prefix and prefill `tail` after them."""
+        t = _i32(tail) if len(tail) else np.zeros(1, dtype=np.int32)
+        pid = C.c_int32()
+        self._check(self.lib.advspec_prefill_extend(self.h, prefix_id, keep_tokens, _p(t, C.c_int32), len(tail),
+                                                    C.byref(pid)))
         return pid.value
 
     def fork(self, prefix_id: int, seeds: Sequence[int]) -> list[int]:

@@ -156,14 +156,18 @@ def _finish(model: str, content: str, input_tokens: int, output_tokens: int) -> 
                          input_tokens=input_tokens, output_tokens=output_tokens, cost=cost)
 
 
-def _report_failure(model: str, attempt: int, last_error: str) -> None:
+def _report_failure(model: str, attempt: int, last_error: str, sleep: bool = True) -> float:
+    """The reference's retry messages (models.py:663-676).  Returns the back-off of this attempt (0 after
+    the last); sleeps it unless the caller does so once for a whole group of opponents."""
     if attempt < MAX_RETRIES - 1:
         delay = RETRY_BASE_DELAY * (2 ** attempt)
         print(f"Warning: {model} failed (attempt {attempt + 1}/{MAX_RETRIES}): {last_error}. "
               f"Retrying in {delay:.1f}s...", file=sys.stderr)
-        time.sleep(delay)
-    else:
-        print(f"Error: {model} failed after {MAX_RETRIES} attempts: {last_error}", file=sys.stderr)
+        if sleep:
+            time.sleep(delay)
+        return delay
+    print(f"Error: {model} failed after {MAX_RETRIES} attempts: {last_error}", file=sys.stderr)
+    return 0.0
 
 
 def call_single_model(model: str, spec: str, round_num: int, doc_type: str, press: bool = False,
@@ -214,9 +218,11 @@ def call_single_model(model: str, spec: str, round_num: int, doc_type: str, pres
 
 
 def _call_local_panel(local: list[tuple[int, str]], spec: str, round_num: int, doc_type: str, press: bool,
-                      focus, persona, context, preserve_intent: bool) -> list[ModelResponse]:
-    """All local opponents of the round in one engine pass per same-weight group; a group that
-    raises is retried as a whole on the reference's schedule, then reported per opponent."""
+                      focus, persona, context, preserve_intent: bool, timeout: int = 600) -> list[ModelResponse]:
+    """All local opponents of the round in one engine pass per same-weight group; opponents whose group
+    raises (or whose name is unknown) are retried together on the reference's schedule — one back-off per
+    attempt, as the reference's threads sleep in parallel — then reported per opponent.  `timeout` bounds
+    each attempt like the per-call timeout of the reference (models.py:621)."""
     system_prompt, user_message = build_messages(spec, round_num, doc_type, press, focus, persona, context,
                                                  preserve_intent)
     names = [m for _, m in local]
@@ -224,8 +230,16 @@ def _call_local_panel(local: list[tuple[int, str]], spec: str, round_num: int, d
     done: dict[int, ModelResponse] = {}
     pending = list(range(len(local)))
     for attempt in range(MAX_RETRIES):
-        outs = runtime.run_round([names[j] for j in pending], system_prompt, user_message,
-                                 [seeds[j] for j in pending], 8000, 0.7)
+        with concurrent.futures.ThreadPoolExecutor(max_workers=1) as one:
+            fut = one.submit(runtime.run_round, [names[j] for j in pending], system_prompt, user_message,
+                             [seeds[j] for j in pending], 8000, 0.7)
+            try:
+                outs = fut.result(timeout=timeout if timeout and timeout > 0 else None)
+            except concurrent.futures.TimeoutError:
+                outs = [TimeoutError(f"local engine round timed out after {timeout}s")] * len(pending)
+                one.shutdown(wait=False, cancel_futures=True)
+            except Exception as ex:  # run_round reports per opponent; anything else fails the attempt as a whole
+                outs = [ex] * len(pending)
         failed: list[int] = []
         for j, out in zip(pending, outs):
             if isinstance(out, Exception):
@@ -235,8 +249,9 @@ def _call_local_panel(local: list[tuple[int, str]], spec: str, round_num: int, d
                 done[j] = _finish(names[j], out.text, out.prompt_tokens, out.completion_tokens)
         if not failed:
             break
-        for j in failed:
-            _report_failure(names[j], attempt, done[j].error or "")
+        delay = max(_report_failure(names[j], attempt, done[j].error or "", sleep=False) for j in failed)
+        if delay > 0:
+            time.sleep(delay)
         pending = failed
     return [done[j] for j in range(len(local))]
 
@@ -257,7 +272,7 @@ def call_models_parallel(models: list[str], spec: str, round_num: int, doc_type:
         futures = []
         if local:
             futures.append(pool.submit(_call_local_panel, local, spec, round_num, doc_type, press, focus,
-                                       persona, context, preserve_intent))
+                                       persona, context, preserve_intent, timeout))
         for _, m in remote:
             futures.append(pool.submit(call_single_model, m, spec, round_num, doc_type, press, focus, persona,
                                        context, preserve_intent, codex_reasoning, codex_search, timeout,

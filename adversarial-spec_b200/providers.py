@@ -112,7 +112,7 @@ def validate_model_credentials(models: list[str]) -> tuple[list[str], list[str]]
     valid, invalid = [], []
     for m in models:
         if is_local_model(m):
-            valid.append(m)
+            (valid if local_model_known(m) else invalid).append(m)
         elif m.startswith("codex/"):
             (valid if CODEX_AVAILABLE else invalid).append(m)
         elif m.startswith("gemini-cli/"):
@@ -123,7 +123,19 @@ def validate_model_credentials(models: list[str]) -> tuple[list[str], list[str]]
     return valid, invalid
 
 
+def local_model_known(model: str) -> bool:
+    from .model_spec import resolve
+
+    try:
+        resolve(model)
+        return True
+    except KeyError:
+        return False
+
+
 def required_key_hint(model: str) -> str:
+    if is_local_model(model):
+        return "unknown local model; known: " + ", ".join("b200/" + n for n in REGISTRY)
     if model.startswith("codex/"):
         return "requires Codex CLI: npm install -g @openai/codex && codex login"
     key = next((k for p, k in _KEY_FOR_PREFIX if model.startswith(p)), None)

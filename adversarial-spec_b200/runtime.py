@@ -60,6 +60,18 @@ def tp_world() -> tuple[int, int]:
     return _env_int("RANK", 0), tp
 
 
+def broadcast_object(obj, src: int = 0):
+    """Plumbing for the tensor-parallel CLI: one Python object from rank `src` to every rank of the
+    torchrun job (gloo; the group is created here if the engine has not created it yet)."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        dist.init_process_group("gloo")
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def create_tp_engine(spec: ModelSpec, device: int, max_prefix_tokens: int, max_new_tokens: int, max_seqs: int,
                      tp_rank: int, tp_size: int) -> eng.Engine:
     """This rank's handle of a tensor-parallel engine: rank 0 draws the NCCL id, torch.distributed
@@ -99,57 +111,229 @@ class Generation:
     decode_ms: float = 0.0
 
 
+class HFTokenizerAdapter:
+    """A model's REAL tokenizer (tokenizers-format `tokenizer.json`) behind the interface the runtime uses.
+    Loaded when a weight blob is served (ADVSPEC_WEIGHTS_DIR/<model>.blob + <model>.tokenizer.json, optional
+    <model>.meta.json with {"eos_token_id", "bos_token_id", "chat_template": "...{system}...{user}...",
+    "rope_inv_freq": [...]}).  Random-init benchmark weights keep the synthetic tokenizer."""
+
+    def __init__(self, tokenizer_json: str, meta: dict, vocab_size: int):
+        from tokenizers import Tokenizer
+
+        self.tk = Tokenizer.from_file(tokenizer_json)
+        if self.tk.get_vocab_size() > vocab_size:
+            raise ValueError(f"{tokenizer_json}: {self.tk.get_vocab_size()} tokens exceed the model's vocabulary "
+                             f"of {vocab_size}")
+        self.vocab_size = vocab_size
+        self.eos_id = int(meta.get("eos_token_id", -1))
+        self.bos_id = meta.get("bos_token_id")
+        self.template = meta.get("chat_template")
+        if self.eos_id < 0:
+            raise ValueError("meta.json must give eos_token_id for a real tokenizer")
+
+    def encode(self, text: str, bos: bool = False) -> list[int]:
+        ids = self.tk.encode(text, add_special_tokens=False).ids
+        return ([int(self.bos_id)] if bos and self.bos_id is not None else []) + ids
+
+    def decode(self, ids) -> str:
+        return self.tk.decode([int(t) for t in ids if int(t) >= 0], skip_special_tokens=True)
+
+    def count(self, text: str) -> int:
+        return len(self.encode(text))
+
+    def render(self, system_prompt: str, user_message: str) -> str:
+        if self.template:
+            return self.template.replace("{system}", system_prompt).replace("{user}", user_message)
+        return render_chat(system_prompt, user_message)
+
+
+def tokenizer_for(spec: ModelSpec):
+    """(tokenizer, meta) for one model: the real one when a weight blob is served, else synthetic.
+    A blob WITHOUT its tokenizer is an error — feeding trained weights synthetic ids produces noise."""
+    wdir = os.environ.get("ADVSPEC_WEIGHTS_DIR")
+    if wdir and os.path.exists(os.path.join(wdir, f"{spec.name}.blob")):
+        tj = os.path.join(wdir, f"{spec.name}.tokenizer.json")
+        mj = os.path.join(wdir, f"{spec.name}.meta.json")
+        if not os.path.exists(tj):
+            raise FileNotFoundError(f"{wdir}/{spec.name}.blob is served but {tj} is missing: a weight blob needs "
+                                    f"its own tokenizer (and {spec.name}.meta.json with eos_token_id)")
+        import json
+
+        meta = json.loads(open(mj).read()) if os.path.exists(mj) else {}
+        return HFTokenizerAdapter(tj, meta, spec.vocab_size), meta
+    return SyntheticTokenizer(spec.vocab_size), {}
+
+
+def render_prompt(tok, system_prompt: str, user_message: str) -> str:
+    return tok.render(system_prompt, user_message) if hasattr(tok, "render") else render_chat(system_prompt, user_message)
+
+
 @dataclass
 class _Resident:
     engine: eng.Engine
-    tok: SyntheticTokenizer
+    tok: object
     lock: threading.Lock = field(default_factory=threading.Lock)
     max_prefix: int = 0
     max_new: int = 0
+    users: int = 0  # callers holding this engine (EnginePool.lease); it is never closed while > 0
 
 
 class EnginePool:
-    """Engines stay resident across calls and rounds (model load would otherwise dominate)."""
+    """Engines stay resident across calls and rounds (model load would otherwise dominate).
+
+    Callers `lease()` an engine for the duration of a round.  An engine that is too small for a new
+    request is replaced only when nobody holds it: the pool waits for its users to drain, so a
+    concurrent round on the same (model, device) can never be handed a destroyed handle."""
 
     def __init__(self):
         self._engines: dict[tuple[str, int], _Resident] = {}
         self._mu = threading.Lock()
+        self._idle = threading.Condition(self._mu)
+        self.created = 0  # engines ever created by this pool (resident.py reports it per invocation)
+
+    def _build(self, spec: ModelSpec, device: int, need_prefix: int, need_new: int) -> _Resident:
+        cap_prefix = max(need_prefix, _env_int("ADVSPEC_MIN_PREFIX", 0))
+        cap_prefix = (cap_prefix + 255) // 256 * 256
+        cap_new = max(need_new, _env_int("ADVSPEC_MIN_NEW", 16))
+        tp_rank, tp_size = tp_world()
+        tok, meta = tokenizer_for(spec)
+        if tp_size > 1:
+            e = create_tp_engine(spec, device, cap_prefix, cap_new, MAX_BATCH, tp_rank, tp_size)
+        else:
+            e = eng.Engine(spec, device, cap_prefix, cap_new, MAX_BATCH)
+        wdir = os.environ.get("ADVSPEC_WEIGHTS_DIR")
+        blob_path = os.path.join(wdir, f"{spec.name}.blob") if wdir else None
+        if blob_path and os.path.exists(blob_path):
+            from .weights import shard_blob
+            e.load_weights(shard_blob(np.fromfile(blob_path, dtype=np.uint8), spec, tp_rank, tp_size))
+            if meta.get("rope_inv_freq"):
+                e.set_rope_inv_freq(np.asarray(meta["rope_inv_freq"], dtype=np.float32))
+        else:
+            e.init_weights_random(_env_int("ADVSPEC_WEIGHT_SEED", 0), 0.02)
+        self.created += 1
+        return _Resident(e, tok, max_prefix=cap_prefix, max_new=cap_new)
+
+    def acquire(self, spec: ModelSpec, device: int, need_prefix: int, need_new: int) -> _Resident:
+        key = (spec.name, device)
+        with self._idle:
+            while True:
+                r = self._engines.get(key)
+                if r is not None and r.max_prefix >= need_prefix and r.max_new >= need_new:
+                    r.users += 1
+                    return r
+                if r is not None and r.users > 0:
+                    self._idle.wait()  # too small, but somebody is inside it: replace it once they are done
+                    continue
+                if r is not None:
+                    del self._engines[key]
+                    PREFIXES.forget(r.engine)
+                    r.engine.close()  # nobody holds it and nobody can get it any more
+                    need_prefix, need_new = max(need_prefix, r.max_prefix), max(need_new, r.max_new)
+                r = self._build(spec, device, need_prefix, need_new)
+                r.users = 1
+                self._engines[key] = r
+                return r
+
+    def release(self, r: _Resident) -> None:
+        with self._idle:
+            r.users -= 1
+            self._idle.notify_all()
+
+    def lease(self, spec: ModelSpec, device: int, need_prefix: int, need_new: int):
+        pool = self
+
+        class _Lease:
+            def __enter__(self_inner):
+                self_inner.r = pool.acquire(spec, device, need_prefix, need_new)
+                return self_inner.r
+
+            def __exit__(self_inner, *exc):
+                pool.release(self_inner.r)
+                return False
+
+        return _Lease()
 
     def get(self, spec: ModelSpec, device: int, need_prefix: int, need_new: int) -> _Resident:
-        key = (spec.name, device)
+        """The resident engine without holding it (measurement code that owns the process)."""
+        r = self.acquire(spec, device, need_prefix, need_new)
+        self.release(r)
+        return r
+
+    def resident_count(self) -> int:
         with self._mu:
-            r = self._engines.get(key)
-            if r is not None and (r.max_prefix < need_prefix or r.max_new < need_new):
-                r.engine.close()
-                r = None
-            if r is None:
-                cap_prefix = max(need_prefix, _env_int("ADVSPEC_MIN_PREFIX", 0))
-                cap_prefix = (cap_prefix + 255) // 256 * 256
-                cap_new = max(need_new, 16)
-                tp_rank, tp_size = tp_world()
-                if tp_size > 1:
-                    e = create_tp_engine(spec, device, cap_prefix, cap_new, MAX_BATCH, tp_rank, tp_size)
-                else:
-                    e = eng.Engine(spec, device, cap_prefix, cap_new, MAX_BATCH)
-                wdir = os.environ.get("ADVSPEC_WEIGHTS_DIR")
-                blob_path = os.path.join(wdir, f"{spec.name}.blob") if wdir else None
-                if blob_path and os.path.exists(blob_path):
-                    from .weights import shard_blob
-                    e.load_weights(shard_blob(np.fromfile(blob_path, dtype=np.uint8), spec, tp_rank, tp_size))
-                else:
-                    e.init_weights_random(_env_int("ADVSPEC_WEIGHT_SEED", 0), 0.02)
-                r = _Resident(e, SyntheticTokenizer(spec.vocab_size), max_prefix=cap_prefix, max_new=cap_new)
-                self._engines[key] = r
-            return r
+            return len(self._engines)
 
     def close(self) -> None:
-        with self._mu:
+        with self._idle:
+            while any(r.users > 0 for r in self._engines.values()):
+                self._idle.wait()
             for r in self._engines.values():
+                PREFIXES.forget(r.engine)
                 r.engine.close()
             self._engines.clear()
 
 
 POOL = EnginePool()
+
+
+class PrefixCache:
+    """Cross-call reuse of the live prefix KV of each resident engine.
+
+    The reference assembles system -> "This is round r" -> spec -> context -> focus -> instruction
+    (prompts.py:233-241), so calls on the same round and document that differ in `--context`, `--focus` or
+    `--preserve-intent` share everything up to the end of the spec.  The engine keeps ONE live prefix; this
+    cache remembers its token ids and, when the next prompt shares at least ADVSPEC_PREFIX_REUSE_MIN (default
+    0.5) of its length with it, prefills only the tail (`advspec_prefill_extend`).  An identical prompt
+    (retry, a panel larger than one batch) is re-armed without any prefill.  Consecutive ROUNDS diverge at
+    the round number, a few hundred tokens in, and are prefilled in full."""
+
+    def __init__(self):
+        self._live: dict[int, tuple[int, np.ndarray]] = {}  # id(engine) -> (prefix id, token ids)
+        self.stats = {"full": 0, "extended": 0, "rearmed": 0, "tokens_reused": 0, "tokens_prefilled": 0}
+
+    def prefill(self, e: eng.Engine, key, prompt_ids: Sequence[int]) -> int:
+        ids = np.asarray(prompt_ids, dtype=np.int32)
+        n = int(ids.size)
+        live = self._live.get(id(e))
+        try:
+            min_frac = float(os.environ.get("ADVSPEC_PREFIX_REUSE_MIN", "0.5"))
+        except ValueError:
+            min_frac = 0.5
+        if live is not None and os.environ.get("ADVSPEC_PREFIX_CACHE", "1") != "0":
+            pid, old = live
+            m = min(n, int(old.size))
+            neq = np.nonzero(ids[:m] != old[:m])[0]
+            lcp = int(neq[0]) if neq.size else m
+            try:
+                if lcp == n and n == old.size:
+                    new = e.prefill_extend(pid, n, [])
+                    self.stats["rearmed"] += 1
+                    self.stats["tokens_reused"] += n
+                    self._live[id(e)] = (new, ids)
+                    return new
+                keep = min(lcp, n - 1)  # at least the last token runs, to produce the next-token logits
+                if keep >= 1 and keep >= min_frac * n:
+                    new = e.prefill_extend(pid, keep, ids[keep:].tolist())
+                    self.stats["extended"] += 1
+                    self.stats["tokens_reused"] += keep
+                    self.stats["tokens_prefilled"] += n - keep
+                    self._live[id(e)] = (new, ids)
+                    return new
+            except eng.EngineError as ex:
+                if ex.status != 4:  # STATE: someone replaced the live prefix behind the cache -> full prefill
+                    raise
+        self._live.pop(id(e), None)
+        new = e.prefill(ids.tolist())
+        self.stats["full"] += 1
+        self.stats["tokens_prefilled"] += n
+        self._live[id(e)] = (new, ids)
+        return new
+
+    def forget(self, e: eng.Engine) -> None:
+        self._live.pop(id(e), None)
+
+
+PREFIXES = PrefixCache()
 
 
 def effective_max_new(max_tokens: int) -> int:
@@ -166,16 +350,15 @@ def opponent_seed(round_num: int, index: int) -> int:
 def generate_group(spec: ModelSpec, device: int, system_prompt: str, user_message: str, n_opponents: int,
                    seeds: Sequence[int], max_tokens: int, temperature: float) -> list[Generation]:
     """One shared-prefix round for `n_opponents` opponents of one model on one GPU."""
-    tok = SyntheticTokenizer(spec.vocab_size)
-    prompt_ids = tok.encode(render_chat(system_prompt, user_message), bos=True)
+    tok, _ = tokenizer_for(spec)
+    prompt_ids = tok.encode(render_prompt(tok, system_prompt, user_message), bos=True)
     max_new = effective_max_new(max_tokens)
-    res = POOL.get(spec, device, len(prompt_ids), max_new)
     out: list[Generation] = []
-    with res.lock:
+    with POOL.lease(spec, device, len(prompt_ids), max_new) as res, res.lock:
         e = res.engine
         for g0 in range(0, n_opponents, MAX_BATCH):
             batch_seeds = list(seeds[g0: g0 + MAX_BATCH])
-            pid = e.prefill(prompt_ids)
+            pid = PREFIXES.prefill(e, (spec.name, device), prompt_ids)
             ids = e.fork(pid, batch_seeds)
             dec = e.decode(ids, max_new, temperature=temperature, eos_id=tok.eos_id)
             tm = e.timing()
@@ -183,7 +366,7 @@ def generate_group(spec: ModelSpec, device: int, system_prompt: str, user_messag
                 body = toks[:-1] if (toks and toks[-1] == tok.eos_id) else toks
                 out.append(Generation(res.tok.decode(body), len(prompt_ids), len(toks), toks,
                                       tm.prefill_ms, tm.decode_ms))
-            e.release_prefix(pid)
+            e.release_seqs(ids)
     return out
 
 
@@ -229,8 +412,17 @@ def run_round(model_names: Sequence[str], system_prompt: str, user_message: str,
     """All local opponents of one critique round.  Returns, per opponent (input order), a
     Generation or the Exception its group raised."""
     devices = list(devices) if devices is not None else visible_devices()
-    plan = plan_placement(model_names, devices)
     results: list = [None] * len(model_names)
+    known: list[int] = []
+    for i, m in enumerate(model_names):  # an unknown local name fails THAT opponent, like a bad provider id
+        try:
+            resolve(m)
+            known.append(i)
+        except KeyError as ex:
+            results[i] = ValueError(str(ex.args[0]) if ex.args else str(ex))
+    plan = plan_placement([model_names[i] for i in known], devices)
+    for p in plan:
+        p.indices = [known[j] for j in p.indices]
 
     def work(p: Placement):
         try:
@@ -242,6 +434,8 @@ def run_round(model_names: Sequence[str], system_prompt: str, user_message: str,
             for i in p.indices:
                 results[i] = ex
 
+    if not plan:
+        return results
     if len(plan) == 1:
         work(plan[0])
     else:

@@ -158,6 +158,17 @@ advspec_status advspec_set_rope_inv_freq(advspec_engine *e,
 advspec_status advspec_prefill(advspec_engine *e, const int32_t *tokens,
                                int32_t n_tokens, int32_t *prefix_id);
 
+/* Continue a live prefix instead of starting over: keep the KV of its first keep_tokens tokens and
+ * prefill `tokens[0..n_tokens)` at positions keep_tokens.. against it.  Serves the reference's prompt
+ * variants that differ only AFTER the spec — `--context`, `--focus`, `--preserve-intent` sections follow
+ * the document in the user message (prompts.py:233-241; models.py:130-146, 485-503) — so a second call on
+ * the same round and document prefills only its tail.  n_tokens == 0 with keep_tokens == the prefix
+ * length re-arms the prefix as is (identical prompt: retries, a panel larger than one batch).  Every
+ * opponent forked from the old prefix is released; the old id dies; returns the new id. */
+advspec_status advspec_prefill_extend(advspec_engine *e, int32_t prefix_id,
+                                      int32_t keep_tokens, const int32_t *tokens,
+                                      int32_t n_tokens, int32_t *new_prefix_id);
+
 /* Fork n opponents over one prefix without copying KV.  seeds[i] drives the
  * sampler of opponent i (the reference gets per-call randomness from the
  * provider at temperature 0.7, models.py:626). */

@@ -112,7 +112,7 @@ def completion(*, model: str, messages: list, max_tokens: int = 8000, timeout=No
     with torch.no_grad():
         _tls.layer_s = 0.0
         t0 = time.perf_counter()
-        r = hf(input_ids=torch.tensor([ids], dtype=torch.long), use_cache=True)
+        r = hf(input_ids=torch.tensor([ids], dtype=torch.long), use_cache=True, logits_to_keep=1)  # as HF generate does
         t_prefill = time.perf_counter() - t0
         layer_prefill = _tls.layer_s
         _tls.layer_s = 0.0
