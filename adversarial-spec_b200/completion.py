@@ -5,7 +5,7 @@ Only the fields the reference reads exist on the response:
 ``.choices[0].message.content`` and ``.usage.prompt_tokens/.completion_tokens``
 (models.py:629, 639-640).  The reference enters this function from N threads at
 once with identical ``messages`` when opponents share a model (models.py:699);
-those calls are coalesced here — the first caller waits until arrivals go quiet (2 ms
+those calls are coalesced here — the first caller waits until arrivals go quiet (5 ms
 without a new sibling, 25 ms at most), then ONE prefill serves them all.  Callers that can see the whole
 panel should use ``models.call_models_parallel`` (seam B2) instead.
 """
@@ -83,10 +83,10 @@ def _env_ms(name: str, default: float) -> float:
 def _gather_siblings(b: "_Batch") -> None:
     """The leader's wait for the sibling calls of one fan-out.  The reference starts its N threads within
     microseconds of each other (models.py:699-719), so the leader does not sit out a fixed window: it
-    returns as soon as no new caller has joined for ADVSPEC_COALESCE_QUIET_MS (default 2 ms), and never
+    returns as soon as no new caller has joined for ADVSPEC_COALESCE_QUIET_MS (default 5 ms), and never
     waits longer than ADVSPEC_COALESCE_MS (default 25 ms) in total."""
     deadline = time.perf_counter() + _env_ms("ADVSPEC_COALESCE_MS", 25.0)
-    quiet = _env_ms("ADVSPEC_COALESCE_QUIET_MS", 2.0)
+    quiet = _env_ms("ADVSPEC_COALESCE_QUIET_MS", 5.0)
     seen, last_change = b.n, time.perf_counter()
     while True:
         now = time.perf_counter()

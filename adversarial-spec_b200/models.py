@@ -230,16 +230,17 @@ def _call_local_panel(local: list[tuple[int, str]], spec: str, round_num: int, d
     done: dict[int, ModelResponse] = {}
     pending = list(range(len(local)))
     for attempt in range(MAX_RETRIES):
-        with concurrent.futures.ThreadPoolExecutor(max_workers=1) as one:
-            fut = one.submit(runtime.run_round, [names[j] for j in pending], system_prompt, user_message,
-                             [seeds[j] for j in pending], 8000, 0.7)
-            try:
-                outs = fut.result(timeout=timeout if timeout and timeout > 0 else None)
-            except concurrent.futures.TimeoutError:
-                outs = [TimeoutError(f"local engine round timed out after {timeout}s")] * len(pending)
-                one.shutdown(wait=False, cancel_futures=True)
-            except Exception as ex:  # run_round reports per opponent; anything else fails the attempt as a whole
-                outs = [ex] * len(pending)
+        one = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+        fut = one.submit(runtime.run_round, [names[j] for j in pending], system_prompt, user_message,
+                         [seeds[j] for j in pending], 8000, 0.7)
+        try:
+            outs = fut.result(timeout=timeout if timeout and timeout > 0 else None)
+        except concurrent.futures.TimeoutError:
+            # a GPU round cannot be cancelled: it finishes in the background (holding its engine lease)
+            outs = [TimeoutError(f"local engine round timed out after {timeout}s")] * len(pending)
+        except Exception as ex:  # run_round reports per opponent; anything else fails the attempt as a whole
+            outs = [ex] * len(pending)
+        one.shutdown(wait=False)
         failed: list[int] = []
         for j, out in zip(pending, outs):
             if isinstance(out, Exception):

@@ -80,3 +80,126 @@ def test_cli_critique_json_on_the_gpu(cuda_device, tmp_path):
     assert all(r["output_tokens"] == 8 and r["error"] is None and r["cost"] == 0.0 for r in out["results"])
     assert out["cost"]["output_tokens"] == 16
     assert "Calling 2 model(s) (critiquing): b200/tiny-llama, b200/tiny-llama..." in p.stderr
+
+
+def test_export_tasks_runs_on_the_engine(cuda_device, tmp_path):
+    """`debate.py export-tasks` is the other `completion` call site (reference
+    debate.py:688-736) — one sequence, temperature 0.3, no retry — here through the CUDA engine."""
+    env = dict(os.environ, ADVSPEC_MAX_NEW_TOKENS="24", ADVSPEC_DEVICES="0", HOME=str(tmp_path))
+    p = subprocess.run([sys.executable, str(ROOT / "adversarial-spec_b200" / "debate.py"), "export-tasks", "--models",
+                        "b200/tiny-llama", "--doc-type", "prd", "--json"],
+                       input=_spec(300), capture_output=True, text=True, env=env, cwd=tmp_path, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert json.loads(p.stdout) == {"tasks": []}, "a random-init model emits no [TASK] blocks"
+    # the same call in-process: one sequence was decoded, sampled at T = 0.3 from the engine's own logits
+    from advspec_b200 import envelope
+    from oracle import sampling_ref
+
+    prompt = envelope.EXPORT_TASKS_PROMPT.format(doc_type_name=envelope.get_doc_type_name("prd"), spec=_spec(300))
+    r = comp.completion(model="b200/tiny-llama", messages=[{"role": "user", "content": prompt}], max_tokens=8000,
+                        temperature=0.3)
+    assert r.usage.completion_tokens == 12 and r.usage.prompt_tokens > 300
+    res = next(iter(runtime.POOL._engines.values()))
+    e = res.engine
+    assert e.timing().decode_batch == 1
+    ids = res.tok.encode(runtime.render_prompt(res.tok, "", prompt), bos=True)
+    pid = e.prefill(ids)
+    lg = e.get_logits(1)[0]
+    seed = runtime.opponent_seed(0, (comp._call_counter - 1) * 16)
+    tok0 = e.decode(e.fork(pid, [seed]), 1, temperature=0.3).tokens[0][0]
+    want, gap = sampling_ref.sample(lg, 0.3, seed, 0)
+    assert tok0 == want or gap < 1e-3
+
+
+def test_prefix_reuse_across_calls_matches_a_full_prefill(cuda_device, diag, monkeypatch):
+    """a second call on the same round and document that only adds a `--focus` / context
+    section after the spec prefills its tail against the kept prefix KV (advspec_prefill_extend).  The
+    logits after the extended prefill must equal a from-scratch prefill of the same prompt (same kernels,
+    another chunking -> accumulation-order noise only) and the HF oracle's."""
+    from oracle import hf_oracle
+    from tests.gpu_util import TOL_MAX, TOL_RMS, make_engine, rel_errors
+    import numpy as np
+
+    spec, model, e = make_engine("tiny-llama-128", 31, max_prefix=2048)
+    rng = np.random.default_rng(3)
+    head = rng.integers(0, spec.vocab_size, 900).tolist()
+    tail_a = rng.integers(0, spec.vocab_size, 40).tolist()
+    tail_b = rng.integers(0, spec.vocab_size, 133).tolist()
+    pid = e.prefill(head + tail_a)
+    t_full = e.timing().prefill_ms
+    pid2 = e.prefill_extend(pid, len(head), tail_b)  # keep 900 tokens (not a multiple of any tile), new tail
+    t_ext = e.timing().prefill_ms
+    got = e.get_logits(1)[0].copy()
+    ref = hf_oracle.hf_logits(model, head + tail_b)[-1]
+    mx, rms = rel_errors(got, ref)
+    scratch_pid = e.prefill(head + tail_b)
+    scratch = e.get_logits(1)[0].copy()
+    mx2, rms2 = rel_errors(got, scratch)
+    diag["prefix_extend/tiny-llama-128"] = {"vs_hf": {"max": mx, "rms": rms}, "vs_scratch": {"max": mx2, "rms": rms2},
+                                            "full_ms": t_full, "extend_ms": t_ext}
+    assert mx < TOL_MAX and rms < TOL_RMS and mx2 < 0.03, (mx, rms, mx2)
+    # decode continues from an extended prefix exactly as from a fresh one
+    pid3 = e.prefill_extend(scratch_pid, len(head), tail_b)
+    ids = e.fork(pid3, [5, 6])
+    e.decode_step(ids, [7, 9])
+    step = e.get_logits(2)
+    ref2 = hf_oracle.hf_logits(model, head + tail_b + [7])[-1]
+    mx3, rms3 = rel_errors(step[0], ref2)
+    assert mx3 < TOL_MAX and rms3 < TOL_RMS, (mx3, rms3)
+    with pytest.raises(Exception):
+        e.prefill_extend(pid, 10, [1, 2])  # a dead prefix id is refused
+    e.close()
+
+    # through the public API: call 2 (= call 1 + a focus section) prefills only its tail
+    monkeypatch.setattr(models.time, "sleep", lambda s: None)
+    doc = _spec(1500)
+    runtime.PREFIXES.stats.update(full=0, extended=0, rearmed=0, tokens_reused=0, tokens_prefilled=0)
+    r1 = models.call_models_parallel(["b200/tiny-llama"] * 2, doc, 3, "tech")
+    r2 = models.call_models_parallel(["b200/tiny-llama"] * 2, doc, 3, "tech", focus="security")
+    st = runtime.PREFIXES.stats
+    assert all(r.error is None for r in r1 + r2)
+    assert (st["full"], st["extended"]) == (1, 1) and st["tokens_reused"] > 1500
+    assert r2[0].input_tokens > r1[0].input_tokens
+
+
+def test_resident_server_keeps_engines_across_cli_invocations(cuda_device, tmp_path):
+    """the reference runs one `debate.py` process per round (`--session`, then
+    `--resume`); with the resident server the second and third invocation find the engine loaded."""
+    import time
+
+    sock = str(tmp_path / "advspec.sock")
+    env = dict(os.environ, ADVSPEC_MAX_NEW_TOKENS="8", ADVSPEC_DEVICES="0", HOME=str(tmp_path))
+    srv = subprocess.Popen([sys.executable, str(ROOT / "adversarial-spec_b200" / "resident.py"), "serve", "--socket", sock],
+                           env=env, cwd=tmp_path, stderr=subprocess.PIPE, text=True)
+    try:
+        for _ in range(600):
+            if os.path.exists(sock):
+                break
+            assert srv.poll() is None, srv.stderr.read()
+            time.sleep(0.1)
+        cli = [sys.executable, str(ROOT / "adversarial-spec_b200" / "debate.py"), "critique", "--json"]
+        cenv = dict(env, ADVSPEC_SERVER=sock)
+        walls = []
+        for i, extra in enumerate((["--models", "b200/tiny-llama,b200/tiny-llama", "--session", "s1"],
+                                   ["--resume", "s1"], ["--resume", "s1"])):
+            t0 = time.perf_counter()
+            p = subprocess.run(cli + extra, input=_spec(200) if i == 0 else "", capture_output=True, text=True,
+                               env=cenv, cwd=tmp_path, timeout=300)
+            walls.append(time.perf_counter() - t0)
+            assert p.returncode == 0, p.stderr[-2000:]
+            out = json.loads(p.stdout)
+            assert out["round"] == i + 1 and out["session"] == "s1" and len(out["results"]) == 2
+            assert all(r["output_tokens"] == 8 and r["error"] is None for r in out["results"])
+        from advspec_b200 import resident
+
+        stats = resident.request(sock, [], op="stats")
+        assert stats == {"engines_resident": 1, "engines_created": 1}, stats
+        sess = json.loads((tmp_path / ".config" / "adversarial-spec" / "sessions" / "s1.json").read_text())
+        assert sess["round"] == 4 and len(sess["history"]) == 3
+        assert sorted(p.name for p in (tmp_path / ".adversarial-spec-checkpoints").glob("*.md")) == \
+            ["s1-round-1.md", "s1-round-2.md", "s1-round-3.md"]
+        resident.request(sock, [], op="shutdown")
+        srv.wait(timeout=60)
+    finally:
+        if srv.poll() is None:
+            srv.terminate()
