@@ -1,7 +1,8 @@
 // attn_decode_mma.cuh — decode attention, second design: one kernel per layer does
 //   RoPE of the new q/k  ->  append k/v to the opponent's private suffix KV
 //   ->  split-KV flash-decoding on tensor cores (mma.sync m16n8k16, bf16)
-//   ->  per-split partial (m, l, o); attn_decode_combine2_kernel (below) merges the splits.
+//   ->  per-split partial (m, l, o); the LAST CTA to finish for an (opponent, KV head) pair merges the
+//       splits itself (arrival counter in global memory) — no separate combine launch.
 // A work item is (KV head, opponent group, KV source): the shared prefix is cut
 // into splits that are read ONCE for all opponents and all query heads of the KV
 // head (up to 16 query rows = one MMA M tile); each opponent's suffix is its own
@@ -38,6 +39,8 @@ struct AttnDecode2Params {
   float* part_m;             // [b*H][n_slots]
   float* part_l;
   float* part_o;             // [b*H][n_slots][DH]
+  unsigned int* arrive;      // [b][Hkv] arrival counters (zero between launches; the last arriver resets its own)
+  __nv_bfloat16* out;        // [b][H*dh] attention output (bf16), written by the last arriver of each (b, kv head)
   int b, H, Hkv, G;
   int opg, n_og, n_splits, n_slots;  // opponents per group, groups per KV head, prefix splits, n_splits+1
   float scale;
@@ -371,6 +374,69 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     }
   }
   phase_mark(5);
+
+  // ---- last-arriver merge of the splits.  Every (opponent, KV head) pair expects n_splits prefix partials
+  // (one per prefix CTA of its group) plus its own suffix partial.  A CTA publishes its rows (fence), bumps
+  // the pair's counter, and whoever brings it to n_slots merges the pair's G query rows over all slots and
+  // writes the bf16 attention output — the partials never wait for another kernel launch.
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_last[16];
+  const int n_pairs = is_prefix ? n_opp : 1;
+  if (tid < n_pairs) {
+    const int bi = is_prefix ? o0 + tid : o0 + (j - p.n_splits);
+    const unsigned int prev = atomicAdd(&p.arrive[bi * p.Hkv + hk], 1u);
+    s_last[tid] = (prev + 1u == (unsigned int)p.n_slots) ? 1u : 0u;
+  }
+  __syncthreads();
+  float* c_w = reinterpret_cast<float*>(sKV);  // [G][n_slots] weights 2^(m_s - M), then per-row 1/L at c_inv
+  for (int pi = 0; pi < n_pairs; ++pi) {
+    if (!s_last[pi]) continue;  // uniform across the CTA
+    __threadfence();            // acquire: the other CTAs' partials are visible past their counter increments
+    const int bi = is_prefix ? o0 + pi : o0 + (j - p.n_splits);
+    const int S = p.n_slots;
+    float* c_inv = c_w + p.G * S;
+    // weights: one warp per query row (rows beyond 8 loop)
+    for (int r = warp; r < p.G; r += 8) {
+      const int64_t row = (int64_t)bi * p.H + hk * p.G + r;
+      float M = -INFINITY;
+      for (int sl = lane; sl < S; sl += 32) M = fmaxf(M, __ldcg(&p.part_m[row * S + sl]));
+      M = warp_max(M);
+      float L = 0.f;
+      for (int sl = lane; sl < S; sl += 32) {
+        const float ms = __ldcg(&p.part_m[row * S + sl]);
+        const float wsl = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
+        c_w[r * S + sl] = wsl;
+        L += __ldcg(&p.part_l[row * S + sl]) * wsl;
+      }
+      L = warp_sum(L);
+      if (lane == 0) c_inv[r] = L > 0.f ? 1.0f / L : 0.f;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < p.G * dhg; idx += 256) {
+      const int r = idx / dhg, d = idx % dhg;
+      const int64_t row = (int64_t)bi * p.H + hk * p.G + r;
+      const float* po = p.part_o + row * S * dhg + d;
+      const float* wr = c_w + r * S;
+      float a[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = 0.f;
+      int sl = 0;
+      for (; sl + 8 <= S; sl += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldcg(po + (int64_t)(sl + q) * dhg);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = fmaf(v[q], wr[sl + q], a[q]);
+      }
+      for (; sl < S; ++sl) a[0] = fmaf(__ldcg(po + (int64_t)sl * dhg), wr[sl], a[0]);
+      const float tot = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+      p.out[row * dhg + d] = __float2bfloat16_rn(tot * c_inv[r]);
+    }
+    if (tid == 0) p.arrive[bi * p.Hkv + hk] = 0u;  // ready for the next layer's launch
+    __syncthreads();
+  }
+  phase_mark(6);
   pdl_launch_dependents();
 }
 

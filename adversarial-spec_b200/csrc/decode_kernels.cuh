@@ -252,6 +252,63 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
     xn[(int64_t)row * d + k] = __float2bfloat16_rn(xr[k] * inv * w[k]);
 }
 
+// Prefill RMSNorm, bandwidth version (d % 4 == 0, d <= 8192): one CTA per row keeps the whole row in
+// registers as 16-byte vectors — the row is read ONCE (fp32, 16 bytes per load), normalised and written as
+// packed bf16 (8 bytes per store).  The scalar kernel above re-read the row and ran at ~2 TB/s on the
+// 5,068 x 4,096 residual stream (60 us x 64 launches per prefill).
+template <int VPT>
+__global__ void __launch_bounds__(256) rmsnorm_vec_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          __nv_bfloat16* __restrict__ xn, int d, float eps) {
+  __shared__ float s_red[8];
+  __shared__ float s_inv;
+  const int row = blockIdx.x, tid = threadIdx.x, n4 = d >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * d);
+  float4 v[VPT];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int k = tid + i * 256;
+    v[i] = k < n4 ? xr[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s_red[i];
+    s_inv = rsqrtf(t / (float)d + eps);
+  }
+  __syncthreads();
+  const float inv = s_inv;
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  uint2* out = reinterpret_cast<uint2*>(xn + (int64_t)row * d);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int k = tid + i * 256;
+    if (k < n4) {
+      const float4 g = w4[k];
+      out[k] = make_uint2(pack_bf16(v[i].x * inv * g.x, v[i].y * inv * g.y),
+                          pack_bf16(v[i].z * inv * g.z, v[i].w * inv * g.w));
+    }
+  }
+}
+
+inline cudaError_t launch_rmsnorm(const float* x, const float* w, __nv_bfloat16* xn, int rows, int d, float eps,
+                                  cudaStream_t st) {
+  const int n4 = d / 4;
+  if (d % 4 == 0 && n4 <= 8 * 256) {
+    if (n4 <= 256) rmsnorm_vec_kernel<1><<<rows, 256, 0, st>>>(x, w, xn, d, eps);
+    else if (n4 <= 512) rmsnorm_vec_kernel<2><<<rows, 256, 0, st>>>(x, w, xn, d, eps);
+    else if (n4 <= 1024) rmsnorm_vec_kernel<4><<<rows, 256, 0, st>>>(x, w, xn, d, eps);
+    else rmsnorm_vec_kernel<8><<<rows, 256, 0, st>>>(x, w, xn, d, eps);
+  } else {
+    rmsnorm_kernel<<<rows, 256, 0, st>>>(x, w, xn, d, eps);
+  }
+  return cudaGetLastError();
+}
+
 // cos/sin table [max_pos][DH/2]: angle = (float)pos * inv_freq[i] in fp32, as
 // HF's rotary embedding does (modeling_llama.py rotary forward), then cosf/sinf.
 __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __restrict__ cs,

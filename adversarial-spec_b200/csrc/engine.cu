@@ -646,6 +646,7 @@ struct advspec_engine {
   float *dx = nullptr, *dx_save = nullptr, *dq = nullptr, *dlogits = nullptr;
   __nv_bfloat16 *dqkv = nullptr, *dattn = nullptr, *dh = nullptr;
   float *part_m = nullptr, *part_l = nullptr, *part_o = nullptr;
+  unsigned int* attn_arrive = nullptr;  // [max_seqs][Hkv] arrival counters of the fused decode attention's merge
   unsigned int* chain_bar = nullptr;  // grid-barrier words of gemv_chain_kernel
   AttnItem* items = nullptr;
   int items_cap = 0, n_items = 0, n_slots = 0;
@@ -836,8 +837,7 @@ advspec_status prefill_chunk(advspec_engine* e, int m, int pos0) {
   e->launches++;
   for (int l = 0; l < d.n_layers; ++l) {
     const LayerW w = layer_w(e, l);
-    rmsnorm_kernel<<<m, 256, 0, e->stream>>>(e->p_x, w.attn_norm, e->p_xn, dm, d.norm_eps);
-    E_CUDA(e, cudaGetLastError());
+    E_CUDA(e, launch_rmsnorm(e->p_x, w.attn_norm, e->p_xn, m, dm, d.norm_eps, e->stream));
     advspec_status s = prefill_gemm(e, e->p_xn, dm, w.wqkv, dm, e->p_qkv, QKV, w.bqkv, m, QKV, dm, EPI_BF16);
     if (s) return s;
     rope_prefill_kernel<<<m, 256, 0, e->stream>>>(e->p_qkv, QKV, prefix_k(e, l), prefix_v(e, l),
@@ -861,8 +861,7 @@ advspec_status prefill_chunk(advspec_engine* e, int m, int pos0) {
     if (s) return s;
     s = tp_allreduce(e, e->p_x, (size_t)m * dm);
     if (s) return s;
-    rmsnorm_kernel<<<m, 256, 0, e->stream>>>(e->p_x, w.mlp_norm, e->p_xn, dm, d.norm_eps);
-    E_CUDA(e, cudaGetLastError());
+    E_CUDA(e, launch_rmsnorm(e->p_x, w.mlp_norm, e->p_xn, m, dm, d.norm_eps, e->stream));
     s = prefill_gemm(e, e->p_xn, dm, w.wgu, dm, e->p_h, d.d_ff, nullptr, m, 2 * d.d_ff, dm, EPI_GATED_BF16);
     if (s) return s;
     s = prefill_gemm(e, e->p_h, d.d_ff, w.wd, d.d_ff, e->p_x, dm, nullptr, m, dm, d.d_ff, tp_resadd_epi(e));
@@ -885,7 +884,7 @@ void free_all(advspec_engine* e) {
   if (e->ar_gen) cudaFree(e->ar_gen);
   void* ptrs[] = {e->w, e->inv_freq, e->rope_cos, e->rope_sin, e->pkv, e->skv, e->p_tokens, e->p_x,
                   e->p_xn, e->p_qkv, e->p_attn, e->p_h, e->prefill_logits, e->dx, e->dx_save, e->dq,
-                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->chain_bar, e->items, e->s_pos, e->kv_maps,
+                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->attn_arrive, e->chain_bar, e->items, e->s_pos, e->kv_maps,
                   e->s_slots, e->s_forced, e->s_seeds, e->s_suf_len, e->s_n_out, e->s_done,
                   e->s_cur_tok, e->s_out, e->samp_pack};
   for (void* p : ptrs)
@@ -1059,6 +1058,8 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       a2.part_m = e->part_m;
       a2.part_l = e->part_l;
       a2.part_o = e->part_o;
+      a2.arrive = e->attn_arrive;
+      a2.out = e->dattn;
       a2.b = b;
       a2.H = d.n_heads;
       a2.Hkv = d.n_kv_heads;
@@ -1071,11 +1072,7 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       a2.dh = d.head_dim;
       E_CUDA(e, launch_attn_decode2(a2, e->a2_ctas, d.head_dim, e->stream, true));
       ADV_TRACE(e->stream, "attn_decode_mma");
-      E_CUDA(e, launch_pdl(attn_decode_combine2_kernel, dim3(b * d.n_heads), dim3(128), 0, e->stream, true,
-                           (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o, e->dattn,
-                           e->n_slots, d.head_dim));
-      ADV_TRACE(e->stream, "attn_combine2");
-      e->launches -= 1;  // two kernels instead of rope + attention + combine (counted as 3 below)
+      e->launches -= 2;  // ONE kernel (RoPE + append + attention + last-arriver merge) instead of the 3 counted below
     } else {
     E_CUDA(e, launch_pdl(rope_decode_kernel, dim3(b), dim3(256), 0, e->stream, true,
                            (const __nv_bfloat16*)e->dqkv, e->dq, suffix_k(e, l), suffix_v(e, l),
@@ -1115,7 +1112,7 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       chain_plan(&cp, b, &xs, &stg);
       E_CUDA(e, launch_chain(cp, b, xs, stg, e->device, e->stream, true));
       ADV_TRACE(e->stream, "gemv chain");
-      e->launches += 4;  // with the -1 above: attention + combine + chain = 3 launches per layer
+      e->launches += 4;  // with the -2 above: attention + chain = 2 launches per layer
       continue;
     }
     GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, tp_resadd_epi(e), d.act, d.norm_eps};
@@ -1384,6 +1381,8 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, dmalloc(&e->part_o, B * d.n_heads * (size_t)(max_splits + 1) * d.head_dim));
     e->items_cap = d.n_kv_heads * (((int)B * G + 3) / 4) * max_splits + (int)B * d.n_kv_heads * ((G + 3) / 4);
     E_CUDA(e, dmalloc(&e->items, (size_t)e->items_cap));
+    E_CUDA(e, dmalloc(&e->attn_arrive, B * (size_t)d.n_kv_heads));
+    E_CUDA(e, cudaMemsetAsync(e->attn_arrive, 0, B * (size_t)d.n_kv_heads * sizeof(unsigned int), e->stream));
     E_CUDA(e, dmalloc(&e->chain_bar, 4));
     E_CUDA(e, cudaMemsetAsync(e->chain_bar, 0, 4 * sizeof(unsigned int), e->stream));
     E_CUDA(e, dmalloc(&e->s_pos, B));
@@ -1673,7 +1672,7 @@ static advspec_status prefill_impl(advspec_engine* e, const int32_t* tokens, int
     st = prefill_chunk(e, m, pos_base + c0);
     if (st != ADVSPEC_OK) break;
     if (all_logits_dev) {
-      rmsnorm_kernel<<<m, 256, 0, e->stream>>>(e->p_x, final_norm_w(e), e->p_xn, d.d_model, d.norm_eps);
+      launch_rmsnorm(e->p_x, final_norm_w(e), e->p_xn, m, d.d_model, d.norm_eps, e->stream);
       st = prefill_gemm(e, e->p_xn, d.d_model, lm_head_w(e), d.d_model,
                         all_logits_dev + (size_t)c0 * d.vocab_size, d.vocab_size, nullptr, m, d.vocab_size,
                         d.d_model, EPI_F32);
@@ -1851,7 +1850,7 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
     key.push_back(e->prefix_gen);
     { int tbits; memcpy(&tbits, &temperature, sizeof tbits); key.push_back(tbits); }
     key.push_back(eos_id);
-    const int64_t per_step = (e->attn_fused ? 6 : 7) * (int64_t)d.n_layers + 3;
+    const int64_t per_step = (e->attn_fused ? 5 : 7) * (int64_t)d.n_layers + 3;
     if (e->use_graph) {
       if (!e->graph || e->graph_key != key) {
         if (e->graph) {
@@ -2250,16 +2249,19 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
   CUtensorMap* dmaps = nullptr;
   int* dpos = nullptr;
   float *pm = nullptr, *plv = nullptr, *po = nullptr;
+  unsigned int* arr = nullptr;
   const size_t nrow = (size_t)b * n_heads * pl.n_slots;
   auto cleanup = [&]() {
     cudaFree(dmaps);
     cudaFree(dpos);
+    cudaFree(arr);
     cudaFree(pm);
     cudaFree(plv);
     cudaFree(po);
   };
   if (cudaMalloc(reinterpret_cast<void**>(&dmaps), sizeof hm) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&dpos), 8 * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&arr), (size_t)b * n_kv_heads * sizeof(unsigned int)) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&pm), nrow * 4) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&plv), nrow * 4) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&po), nrow * head_dim * 4) != cudaSuccess) {
@@ -2269,6 +2271,7 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
   }
   cudaMemcpy(dmaps, hm, sizeof hm, cudaMemcpyHostToDevice);
   cudaMemcpy(dpos, pos_host, b * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemset(arr, 0, (size_t)b * n_kv_heads * sizeof(unsigned int));
   AttnDecode2Params a2{};
   a2.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
   a2.rope_cos = reinterpret_cast<const float*>(rope_cos);
@@ -2286,6 +2289,8 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
   a2.part_m = pm;
   a2.part_l = plv;
   a2.part_o = po;
+  a2.arrive = arr;
+  a2.out = reinterpret_cast<__nv_bfloat16*>(out);
   a2.b = b;
   a2.H = n_heads;
   a2.Hkv = n_kv_heads;
@@ -2297,10 +2302,11 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
   a2.scale = 1.0f / sqrtf((float)head_dim);
   a2.dh = head_dim;
   cudaError_t r = launch_attn_decode2(a2, pl.ctas, head_dim, 0, false);
-  if (r == cudaSuccess)
-    r = launch_pdl(attn_decode_combine2_kernel, dim3(b * n_heads), dim3(128), 0, (cudaStream_t)0, false,
-                   (const float*)pm, (const float*)plv, (const float*)po, reinterpret_cast<__nv_bfloat16*>(out),
-                   pl.n_slots, (int)head_dim);
+  if (r == cudaSuccess) {
+    // run it twice: the second launch appends the same row again and must find the arrival counters reset
+    cudaMemset(out, 0xff, (size_t)b * n_heads * head_dim * 2);
+    r = launch_attn_decode2(a2, pl.ctas, head_dim, 0, false);
+  }
   if (r != cudaSuccess) {
     cleanup();
     g_create_error = std::string("op_attn_decode launch: ") + cudaGetErrorString(r);

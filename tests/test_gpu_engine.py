@@ -193,8 +193,8 @@ def test_kernel_timeline_accounts_for_every_decode_kernel(cuda_device, diag):
     tl = measure.summarize(e.ktrace_read(), spec.n_layers)
     e.ktrace_enable(False)
     e.close()
-    # merge + L x (qkv, attention, combine, o, gate_up, down) + lm_head + vocabulary scan
-    assert tl["kernels_per_step"] == 6 * spec.n_layers + 3, tl
+    # merge + L x (qkv, attention incl. its split merge, o, gate_up, down) + lm_head + vocabulary scan
+    assert tl["kernels_per_step"] == 5 * spec.n_layers + 3, tl
     assert tl["gemv_launches_per_step"] == 4 * spec.n_layers + 1
     assert tl["steps"] >= 8 and tl["us_per_step"] > 0
 

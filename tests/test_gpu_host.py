@@ -177,11 +177,12 @@ def test_resident_server_keeps_engines_across_cli_invocations(cuda_device, tmp_p
                 break
             assert srv.poll() is None, srv.stderr.read()
             time.sleep(0.1)
-        cli = [sys.executable, str(ROOT / "adversarial-spec_b200" / "debate.py"), "critique", "--json"]
+        # (like the reference, `--resume` without `--models` needs a provider key for the default model)
+        cli = [sys.executable, str(ROOT / "adversarial-spec_b200" / "debate.py"), "critique", "--json",
+               "--models", "b200/tiny-llama,b200/tiny-llama"]
         cenv = dict(env, ADVSPEC_SERVER=sock)
         walls = []
-        for i, extra in enumerate((["--models", "b200/tiny-llama,b200/tiny-llama", "--session", "s1"],
-                                   ["--resume", "s1"], ["--resume", "s1"])):
+        for i, extra in enumerate((["--session", "s1"], ["--resume", "s1"], ["--resume", "s1"])):
             t0 = time.perf_counter()
             p = subprocess.run(cli + extra, input=_spec(200) if i == 0 else "", capture_output=True, text=True,
                                env=cenv, cwd=tmp_path, timeout=300)
