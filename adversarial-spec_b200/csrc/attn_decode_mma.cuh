@@ -1,8 +1,15 @@
 // attn_decode_mma.cuh — decode attention, second design: one kernel per layer does
 //   RoPE of the new q/k  ->  append k/v to the opponent's private suffix KV
 //   ->  split-KV flash-decoding on tensor cores (mma.sync m16n8k16, bf16)
-//   ->  per-split partial (m, l, o); the LAST CTA to finish for an (opponent, KV head) pair merges the
-//       splits itself (arrival counter in global memory) — no separate combine launch.
+//   ->  per-split partial (m, l, o).  Two ways to merge the splits:
+//       CL = true : the CTAs of one (KV head, opponent group) — its prefix splits and its suffix items —
+//                   are ONE thread-block cluster; each leaves its (m, l, o) in shared memory and, after a
+//                   cluster barrier, every CTA merges its slice of the head dimensions from its peers'
+//                   shared memory (DSMEM) and writes the bf16 attention output.  No partials in global
+//                   memory, no second kernel.
+//       CL = false: partials go to global memory and attn_decode_combine2_kernel (below) merges them —
+//                   for shapes whose groups do not map onto clusters of 8 or 16 CTAs (one KV head per
+//                   tensor-parallel rank: 147 splits; 32 MHA heads: more groups than clusters fit).
 // A work item is (KV head, opponent group, KV source): the shared prefix is cut
 // into splits that are read ONCE for all opponents and all query heads of the KV
 // head (up to 16 query rows = one MMA M tile); each opponent's suffix is its own
@@ -12,6 +19,8 @@
 // Head dims 64 / 128 / 256 natively, 96 in the 128-wide tile with zero padding.
 // Replaces rope_decode_kernel + attn_decode_kernel + attn_decode_combine_kernel.
 #pragma once
+
+#include <cooperative_groups.h>
 
 #include "attn.cuh"
 #include "common.cuh"
@@ -36,18 +45,19 @@ struct AttnDecode2Params {
   const int* pos_b;          // [b] absolute position of each opponent's new token (device state)
   int slots[8];              // batch index -> opponent slot (fixed for the decode call)
   int prefix_len;
-  float* part_m;             // [b*H][n_slots]
+  float* part_m;             // [b*H][n_slots]                  (CL = false)
   float* part_l;
   float* part_o;             // [b*H][n_slots][DH]
-  unsigned int* arrive;      // [b][Hkv] arrival counters (zero between launches; the last arriver resets its own)
-  __nv_bfloat16* out;        // [b][H*dh] attention output (bf16), written by the last arriver of each (b, kv head)
+  __nv_bfloat16* out;        // [b][H*dh] attention output    (CL = true)
+  int csize;                 // cluster size = n_splits + sfx_slots (CL = true)
+  int sfx_slots;             // suffix items per group in the grid (CL = false: opg; CL = true: min(opg, b))
   int b, H, Hkv, G;
   int opg, n_og, n_splits, n_slots;  // opponents per group, groups per KV head, prefix splits, n_splits+1
   float scale;
   int dh;                    // head_dim in GLOBAL memory (<= DH): Phi-3's 96 runs in the 128-wide tile, zero-padded
 };
 
-template <int DH, int NST>
+template <int DH, int NST, bool CL>
 __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Params p) {
   constexpr int BN = 64;
   constexpr int CPR = DH / 8;
@@ -82,21 +92,27 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   // suffix CTAs backfill behind them, instead of a second wave that again contains full-length prefix CTAs.
   const int n_prefix = p.Hkv * p.n_og * p.n_splits;
   int grp, j;
-  if ((int)blockIdx.x < n_prefix) {
+  if constexpr (CL) {  // a cluster = the items of one group: rank j < n_splits is a prefix split, the rest suffix items
+    grp = blockIdx.x / p.csize;
+    j = blockIdx.x % p.csize;
+  } else if ((int)blockIdx.x < n_prefix) {
     grp = blockIdx.x / p.n_splits;
     j = blockIdx.x % p.n_splits;
   } else {
     const int r = blockIdx.x - n_prefix;
-    grp = r / p.opg;
-    j = p.n_splits + r % p.opg;
+    grp = r / p.sfx_slots;
+    j = p.n_splits + r % p.sfx_slots;
   }
   const int hk = grp / p.n_og, og = grp % p.n_og;
   const int o0 = og * p.opg;
   const int n_opp = min(p.opg, p.b - o0);
   const bool is_prefix = j < p.n_splits;
-  if (!is_prefix && (j - p.n_splits) >= n_opp) return;  // padding item of a short last group
+  // padding item of a short last group: nothing to do — but a cluster member must still meet its peers at the
+  // cluster barriers, so it runs through with an empty key range
+  const bool idle = !is_prefix && (j - p.n_splits) >= n_opp;
+  if (!CL && idle) return;
   const int row_off = is_prefix ? 0 : (j - p.n_splits) * p.G;  // rows inside the group's 16-row tile
-  const int n_rows = is_prefix ? n_opp * p.G : p.G;
+  const int n_rows = idle ? 0 : (is_prefix ? n_opp * p.G : p.G);
   const int slot_out = is_prefix ? j : p.n_splits;
 
   if (tid == 0) {
@@ -112,6 +128,12 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     vb = p.pv + (int64_t)hk * p.pstride * dhg;
     tb = (int)((int64_t)p.prefix_len * j / p.n_splits);
     te = (int)((int64_t)p.prefix_len * (j + 1) / p.n_splits);
+  } else if (idle) {
+    pdl_wait();
+    kb = p.sk;
+    vb = p.sv;
+    tb = 0;
+    te = 0;
   } else {
     pdl_wait();  // needs this step's projections and positions
     // append the new token's k (rotated) and v to this opponent's suffix, then attend over it
@@ -359,82 +381,71 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     s_ML[2 * tid + 1] = L;
   }
   __syncthreads();
-  for (int idx = tid; idx < n_rows * dhg; idx += 256) {
-    const int r = idx / dhg, d = idx % dhg;
-    float O = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) O += s_o[(w * 16 + r) * OP + d] * s_c[w * 16 + r];
-    const int gr = row_off + r;
-    const int bi = o0 + gr / p.G, head = hk * p.G + gr % p.G;
-    const int64_t ps = ((int64_t)bi * p.H + head) * p.n_slots + slot_out;
-    p.part_o[ps * dhg + d] = O;
-    if (d == 0) {
-      p.part_m[ps] = s_ML[2 * r];
-      p.part_l[ps] = s_ML[2 * r + 1];
-    }
-  }
-  phase_mark(5);
-
-  // ---- last-arriver merge of the splits.  Every (opponent, KV head) pair expects n_splits prefix partials
-  // (one per prefix CTA of its group) plus its own suffix partial.  A CTA publishes its rows (fence), bumps
-  // the pair's counter, and whoever brings it to n_slots merges the pair's G query rows over all slots and
-  // writes the bf16 attention output — the partials never wait for another kernel launch.
-  __threadfence();
-  __syncthreads();
-  __shared__ unsigned int s_last[16];
-  const int n_pairs = is_prefix ? n_opp : 1;
-  if (tid < n_pairs) {
-    const int bi = is_prefix ? o0 + tid : o0 + (j - p.n_splits);
-    const unsigned int prev = atomicAdd(&p.arrive[bi * p.Hkv + hk], 1u);
-    s_last[tid] = (prev + 1u == (unsigned int)p.n_slots) ? 1u : 0u;
-  }
-  __syncthreads();
-  float* c_w = reinterpret_cast<float*>(sKV);  // [G][n_slots] weights 2^(m_s - M), then per-row 1/L at c_inv
-  for (int pi = 0; pi < n_pairs; ++pi) {
-    if (!s_last[pi]) continue;  // uniform across the CTA
-    __threadfence();            // acquire: the other CTAs' partials are visible past their counter increments
-    const int bi = is_prefix ? o0 + pi : o0 + (j - p.n_splits);
-    const int S = p.n_slots;
-    float* c_inv = c_w + p.G * S;
-    // weights: one warp per query row (rows beyond 8 loop)
-    for (int r = warp; r < p.G; r += 8) {
-      const int64_t row = (int64_t)bi * p.H + hk * p.G + r;
-      float M = -INFINITY;
-      for (int sl = lane; sl < S; sl += 32) M = fmaxf(M, __ldcg(&p.part_m[row * S + sl]));
-      M = warp_max(M);
-      float L = 0.f;
-      for (int sl = lane; sl < S; sl += 32) {
-        const float ms = __ldcg(&p.part_m[row * S + sl]);
-        const float wsl = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
-        c_w[r * S + sl] = wsl;
-        L += __ldcg(&p.part_l[row * S + sl]) * wsl;
-      }
-      L = warp_sum(L);
-      if (lane == 0) c_inv[r] = L > 0.f ? 1.0f / L : 0.f;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < p.G * dhg; idx += 256) {
+  if constexpr (!CL) {
+    for (int idx = tid; idx < n_rows * dhg; idx += 256) {
       const int r = idx / dhg, d = idx % dhg;
-      const int64_t row = (int64_t)bi * p.H + hk * p.G + r;
-      const float* po = p.part_o + row * S * dhg + d;
-      const float* wr = c_w + r * S;
-      float a[8];
+      float O = 0.f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) a[q] = 0.f;
-      int sl = 0;
-      for (; sl + 8 <= S; sl += 8) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = __ldcg(po + (int64_t)(sl + q) * dhg);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) a[q] = fmaf(v[q], wr[sl + q], a[q]);
+      for (int w = 0; w < 8; ++w) O += s_o[(w * 16 + r) * OP + d] * s_c[w * 16 + r];
+      const int gr = row_off + r;
+      const int bi = o0 + gr / p.G, head = hk * p.G + gr % p.G;
+      const int64_t ps = ((int64_t)bi * p.H + head) * p.n_slots + slot_out;
+      p.part_o[ps * dhg + d] = O;
+      if (d == 0) {
+        p.part_m[ps] = s_ML[2 * r];
+        p.part_l[ps] = s_ML[2 * r + 1];
       }
-      for (; sl < S; ++sl) a[0] = fmaf(__ldcg(po + (int64_t)sl * dhg), wr[sl], a[0]);
-      const float tot = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-      p.out[row * dhg + d] = __float2bfloat16_rn(tot * c_inv[r]);
     }
-    if (tid == 0) p.arrive[bi * p.Hkv + hk] = 0u;  // ready for the next layer's launch
-    __syncthreads();
+  } else {
+    // ---- cluster merge through distributed shared memory
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    float* c_ML = s_ML + 32;       // [16][2]  this CTA's merged (M, L) per local row (M = -inf: no keys)
+    float* c_O = c_ML + 32;        // [16][DH] this CTA's merged, un-normalised output rows
+    for (int idx = tid; idx < 16 * DH; idx += 256) {
+      const int r = idx / DH, d = idx % DH;
+      float O = 0.f;
+      if (r < n_rows) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) O += s_o[(w * 16 + r) * OP + d] * s_c[w * 16 + r];
+      }
+      c_O[idx] = O;
+    }
+    if (tid < 16) {
+      c_ML[2 * tid] = tid < n_rows ? s_ML[2 * tid] : -INFINITY;
+      c_ML[2 * tid + 1] = tid < n_rows ? s_ML[2 * tid + 1] : 0.f;
+    }
+    cluster.sync();  // every member's (M, L, O) is in its shared memory
+    phase_mark(5);
+    // this CTA merges head dimensions [j * DH / csize, (j + 1) * DH / csize) of every row of the group
+    const int dpc = DH / p.csize;
+    const int g_rows = n_opp * p.G;
+    for (int idx = tid; idx < g_rows * dpc; idx += 256) {
+      const int gr = idx / dpc, d = j * dpc + idx % dpc;
+      const int sfx_rank = p.n_splits + gr / p.G, sfx_row = gr % p.G;
+      float M = -INFINITY;
+      for (int c = 0; c <= p.n_splits; ++c) {
+        const int rank = c < p.n_splits ? c : sfx_rank;
+        const float* pml = cluster.map_shared_rank(c_ML, rank);
+        M = fmaxf(M, pml[2 * (c < p.n_splits ? gr : sfx_row)]);
+      }
+      float L = 0.f, O = 0.f;
+      for (int c = 0; c <= p.n_splits; ++c) {
+        const int rank = c < p.n_splits ? c : sfx_rank;
+        const int lr = c < p.n_splits ? gr : sfx_row;
+        const float* pml = cluster.map_shared_rank(c_ML, rank);
+        const float* po = cluster.map_shared_rank(c_O, rank);
+        const float mc = pml[2 * lr];
+        const float wc = (mc == -INFINITY) ? 0.f : exp2f(mc - M);
+        L = fmaf(pml[2 * lr + 1], wc, L);
+        O = fmaf(po[lr * DH + d], wc, O);
+      }
+      if (d < dhg) {
+        const int bi = o0 + gr / p.G, head = hk * p.G + gr % p.G;
+        p.out[((int64_t)bi * p.H + head) * dhg + d] = __float2bfloat16_rn(L > 0.f ? O / L : 0.f);
+      }
+    }
+    cluster.sync();  // nobody leaves while a peer still reads its shared memory
   }
   phase_mark(6);
   pdl_launch_dependents();

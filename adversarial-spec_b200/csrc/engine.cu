@@ -235,9 +235,44 @@ cudaError_t set_smem(K kernel, int bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
+int g_gemm_band_mb = 48;   // ADVSPEC_GEMM_BAND_MB: A-operand bytes of one raster band (0 = one band, the old walk)
+int g_gemm_splitk = 1;     // ADVSPEC_GEMM_SPLITK=0 turns the K-split of the last partial wave off
+constexpr int kGemmSemWords = 256;  // ordering words a caller provides for the K-split tail
+
+// Tile order and tail split of one launch (see gemm_tcgen05.cuh): bands of m-tiles whose A rows stay in L2;
+// when the last wave of the persistent grid is partial and the epilogue accumulates in fp32, its tiles are
+// cut along K among the idle SMs.
+void gemm_schedule(GemmParams* p, int BN, int epi, int grid, unsigned int* sem) {
+  const int num_m = (p->M + kGemmBM - 1) / kGemmBM, num_n = (p->N + BN - 1) / BN;
+  const int num_kb = (p->K + kGemmBK - 1) / kGemmBK;
+  const int tiles = num_m * num_n;
+  int band = num_m;
+  if (g_gemm_band_mb > 0) {
+    const int64_t per_tile = (int64_t)kGemmBM * p->K * 2;
+    const int bm_max = (int)std::max<int64_t>(4, ((int64_t)g_gemm_band_mb << 20) / std::max<int64_t>(per_tile, 1));
+    const int n_bands = (num_m + bm_max - 1) / bm_max;
+    band = (num_m + n_bands - 1) / n_bands;
+  }
+  p->band_m = std::max(1, band);
+  p->full_items = tiles;
+  p->split = 1;
+  p->sem = nullptr;
+  const int tail = tiles % grid;
+  if (g_gemm_splitk && sem && (epi == EPI_RESADD_F32 || epi == EPI_F32) && tiles > grid && tail > 0 &&
+      tail <= kGemmSemWords) {
+    const int split = std::min(std::min(grid / tail, 4), num_kb / 8);
+    if (split >= 2) {
+      p->full_items = tiles - tail;
+      p->split = split;
+      p->sem = sem;
+    }
+  }
+  p->total_items = p->full_items + (tiles - p->full_items) * p->split;
+}
+
 template <int BN, int EPI>
-cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int device,
-                          cudaStream_t st) {
+cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int device,
+                          cudaStream_t st, unsigned int* sem) {
   auto kern = gemm_tc_kernel<BN, EPI>;
   {  // function attributes are per device: set on every launch (host-side, microseconds)
     cudaError_t e = set_smem(kern, GemmCfg<BN>::kSmemBytes);
@@ -245,6 +280,7 @@ cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   }
   const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * ((p.N + BN - 1) / BN);
   const int grid = std::min(tiles, num_sms(device));
+  gemm_schedule(&p, BN, EPI, grid, sem);
   kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ta, tb, p);
   return cudaGetLastError();
 }
@@ -254,7 +290,8 @@ bool g_attn_prefill_tc = true;  // ADVSPEC_ATTN_PREFILL_TC=0 falls back to the m
 
 // C = A[M,K] * B[N,K]^T on tcgen05.  A rows / B rows are the TMA extents.
 cudaError_t launch_gemm(const void* A, int64_t lda, int64_t a_rows, const void* B, int64_t ldb,
-                        const GemmParams& p, int epi, int device, cudaStream_t st, std::string* err) {
+                        const GemmParams& p, int epi, int device, cudaStream_t st, std::string* err,
+                        unsigned int* sem = nullptr) {
   if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) ||
       (reinterpret_cast<uintptr_t>(B) & 15)) {
     if (err) *err = "gemm: operands must be 16-byte aligned with pitches that are multiples of 8";
@@ -279,8 +316,8 @@ cudaError_t launch_gemm(const void* A, int64_t lda, int64_t a_rows, const void* 
   }
 #define ADV_GEMM_CASE(E)                                                   \
   case E:                                                                  \
-    return wide ? launch_gemm_t<256, E>(ta, tb, p, device, st)            \
-                : launch_gemm_t<128, E>(ta, tb, p, device, st);
+    return wide ? launch_gemm_t<256, E>(ta, tb, p, device, st, sem)       \
+                : launch_gemm_t<128, E>(ta, tb, p, device, st, sem);
   switch (epi) {
     ADV_GEMM_CASE(EPI_BF16)
     ADV_GEMM_CASE(EPI_RESADD_F32)
@@ -577,33 +614,58 @@ cudaError_t launch_attn_decode(const AttnDecodeParams& p, int n_items, int DH, c
 
 int g_attn_impl = 2;  // 2: fused tensor-core decode attention (default); 1: scalar 3-kernel path (A/B, other head dims)
 
+// dynamic shared memory of attn_decode_mma_kernel<DH, NST>: query tile + K/V ring + alignment slack + barriers
+int attn2_smem_bytes(int DH) {
+  if (DH == 256) return 16 * 256 * 2 + 3 * 2 * 64 * 256 * 2 + 1024 + 128;
+  if (DH == 64) return 16 * 64 * 2 + 6 * 2 * 64 * 64 * 2 + 1024 + 128;
+  return 16 * 128 * 2 + 6 * 2 * 64 * 128 * 2 + 1024 + 128;
+}
+
+template <int DH, int NST, bool CL>
+cudaError_t launch_attn_decode2_t(const AttnDecode2Params& p, int n_ctas, int smem, cudaStream_t st, bool pdl) {
+  auto kern = attn_decode_mma_kernel<DH, NST, CL>;
+  {  // function attributes are per device: set on every launch (host-side, microseconds)
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+  }
+  if (!CL) return launch_pdl(kern, dim3(n_ctas), dim3(256), smem, st, pdl, p);
+  if (p.csize > 8) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_ctas);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = p.csize;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && g_use_pdl) ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 cudaError_t launch_attn_decode2(const AttnDecode2Params& p, int n_ctas, int DH, cudaStream_t st, bool pdl) {
-  constexpr int NST = 6;
-  dim3 g(n_ctas), blk(256);
+  const bool cl = p.csize > 0;
   if (DH == 128 || DH == 96) {  // 96 (Phi-3): the 128-wide tile with zero padding, p.dh = 96
-    const int smem = 16 * 128 * 2 + NST * 2 * 64 * 128 * 2 + 1024 + 128;  // + alignment slack + barriers
-    {  // function attributes are per device: set on every launch (host-side, microseconds)
-      cudaError_t e = set_smem(attn_decode_mma_kernel<128, NST>, smem);
-      if (e != cudaSuccess) return e;
-    }
-    return launch_pdl(attn_decode_mma_kernel<128, NST>, g, blk, smem, st, pdl, p);
+    const int smem = attn2_smem_bytes(128);
+    return cl ? launch_attn_decode2_t<128, 6, true>(p, n_ctas, smem, st, pdl)
+              : launch_attn_decode2_t<128, 6, false>(p, n_ctas, smem, st, pdl);
   }
   if (DH == 256) {  // Gemma: 64 KB per K+V tile pair, three stages
-    constexpr int NS3 = 3;
-    const int smem = 16 * 256 * 2 + NS3 * 2 * 64 * 256 * 2 + 1024 + 128;
-    {
-      cudaError_t e = set_smem(attn_decode_mma_kernel<256, NS3>, smem);
-      if (e != cudaSuccess) return e;
-    }
-    return launch_pdl(attn_decode_mma_kernel<256, NS3>, g, blk, smem, st, pdl, p);
+    const int smem = attn2_smem_bytes(256);
+    return cl ? launch_attn_decode2_t<256, 3, true>(p, n_ctas, smem, st, pdl)
+              : launch_attn_decode2_t<256, 3, false>(p, n_ctas, smem, st, pdl);
   }
   if (DH == 64) {
-    const int smem = 16 * 64 * 2 + NST * 2 * 64 * 64 * 2 + 1024 + 128;
-    {  // function attributes are per device: set on every launch (host-side, microseconds)
-      cudaError_t e = set_smem(attn_decode_mma_kernel<64, NST>, smem);
-      if (e != cudaSuccess) return e;
-    }
-    return launch_pdl(attn_decode_mma_kernel<64, NST>, g, blk, smem, st, pdl, p);
+    const int smem = attn2_smem_bytes(64);
+    return cl ? launch_attn_decode2_t<64, 6, true>(p, n_ctas, smem, st, pdl)
+              : launch_attn_decode2_t<64, 6, false>(p, n_ctas, smem, st, pdl);
   }
   return cudaErrorInvalidValue;
 }
@@ -646,12 +708,13 @@ struct advspec_engine {
   float *dx = nullptr, *dx_save = nullptr, *dq = nullptr, *dlogits = nullptr;
   __nv_bfloat16 *dqkv = nullptr, *dattn = nullptr, *dh = nullptr;
   float *part_m = nullptr, *part_l = nullptr, *part_o = nullptr;
-  unsigned int* attn_arrive = nullptr;  // [max_seqs][Hkv] arrival counters of the fused decode attention's merge
   unsigned int* chain_bar = nullptr;  // grid-barrier words of gemv_chain_kernel
+  unsigned int* gemm_sem = nullptr;   // ordering words of the prefill GEMM's K-split tail (zero between launches)
   AttnItem* items = nullptr;
   int items_cap = 0, n_items = 0, n_slots = 0;
   // fused tensor-core decode attention: work decomposition of the current batch
   int a2_opg = 1, a2_n_og = 1, a2_n_splits = 1, a2_ctas = 0;
+  int a2_cluster = 0, a2_sfx = 1;  // cluster size (0: splits merged by the combine kernel), suffix items per group
   int h_slots[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int* s_pos = nullptr;     // [max_seqs] absolute position of each batch entry's next token
   CUtensorMap* kv_maps = nullptr;  // [L][2] device copies: prefix K / V tensor maps of each layer
@@ -817,7 +880,7 @@ advspec_status prefill_gemm(advspec_engine* e, const __nv_bfloat16* A, int64_t l
     std::string why;
     // the activation buffers hold C rows, so the TMA extent may cover whole 128-row tiles
     const int64_t a_rows = std::min<int64_t>((M + kGemmBM - 1) / kGemmBM * kGemmBM, e->C);
-    cudaError_t r = launch_gemm(A, lda, a_rows, B, ldb, p, epi, e->device, e->stream, &why);
+    cudaError_t r = launch_gemm(A, lda, a_rows, B, ldb, p, epi, e->device, e->stream, &why, e->gemm_sem);
     if (r != cudaSuccess) {
       e->fail("prefill gemm M=%d N=%d K=%d failed: %s %s", M, N, K, cudaGetErrorString(r), why.c_str());
       return ADVSPEC_ERR_CUDA;
@@ -884,7 +947,7 @@ void free_all(advspec_engine* e) {
   if (e->ar_gen) cudaFree(e->ar_gen);
   void* ptrs[] = {e->w, e->inv_freq, e->rope_cos, e->rope_sin, e->pkv, e->skv, e->p_tokens, e->p_x,
                   e->p_xn, e->p_qkv, e->p_attn, e->p_h, e->prefill_logits, e->dx, e->dx_save, e->dq,
-                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->attn_arrive, e->chain_bar, e->items, e->s_pos, e->kv_maps,
+                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->chain_bar, e->gemm_sem, e->items, e->s_pos, e->kv_maps,
                   e->s_slots, e->s_forced, e->s_seeds, e->s_suf_len, e->s_n_out, e->s_done,
                   e->s_cur_tok, e->s_out, e->samp_pack};
   for (void* p : ptrs)
@@ -950,12 +1013,76 @@ void build_items(advspec_engine* e, const std::vector<int>& slots, std::vector<A
 // shared by the whole group (one CTA per SM in total), each opponent's suffix is its own CTA.
 struct Attn2Plan {
   int opg, n_og, n_splits, ctas, n_slots;
+  int cluster;  // > 0: the items of a group form a thread-block cluster of this size (merge through DSMEM)
+  int sfx;      // suffix items per group in the grid
 };
-Attn2Plan plan_attn2_shape(int b, int n_heads, int n_kv_heads, int prefix_len, int device) {
+
+template <int DH, int NST>
+int max_clusters_of(int csize, int smem) {
+  auto kern = attn_decode_mma_kernel<DH, NST, true>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0;
+  if (csize > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(csize);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csize;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+// How many clusters of `csize` CTAs of the decode attention kernel the device holds at once (cached per
+// device, head_dim and cluster size; 0 when that cluster size cannot be launched).
+int attn2_max_clusters(int device, int DH, int csize) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int>, int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  const auto key = std::make_tuple(device, DH, csize);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  const int smem = attn2_smem_bytes(DH);
+  if (DH == 256) n = max_clusters_of<256, 3>(csize, smem);
+  else if (DH == 64) n = max_clusters_of<64, 6>(csize, smem);
+  else n = max_clusters_of<128, 6>(csize, smem);
+  cache[key] = n;
+  return n;
+}
+
+int g_attn_cluster = 1;  // ADVSPEC_ATTN_IMPL=3 keeps the split + combine-kernel path everywhere (A/B)
+
+Attn2Plan plan_attn2_shape(int b, int n_heads, int n_kv_heads, int head_dim, int prefix_len, int device) {
   const int G = n_heads / n_kv_heads;
   const int opg = std::max(1, 16 / G);
   const int n_og = (b + opg - 1) / opg;
   const int groups = n_kv_heads * n_og;
+  const int DH = head_dim == 96 ? 128 : head_dim;
+  // Cluster path: a group's prefix splits and suffix items are one cluster of 16 or 8 CTAs, the whole grid
+  // resident at once.  (One KV head per tensor-parallel rank gives a single group — 16 CTAs cannot stream a
+  // 32K-token prefix; 32 MHA heads give more groups than clusters fit: both keep the combine kernel.)
+  const int sfx_c = std::min(opg, b);
+  if (g_attn_cluster) {
+    for (int C : {16, 8}) {
+      const int n_splits = C - sfx_c;
+      if (n_splits < 1 || n_splits > prefix_len || DH % C != 0) continue;
+      if (groups * C > num_sms(device)) continue;
+      if (groups * C < 48 && prefix_len >= 2048) continue;  // too few CTAs to stream a long prefix: split finer below
+      if (attn2_max_clusters(device, DH, C) < groups) continue;
+      return Attn2Plan{opg, n_og, n_splits, groups * C, n_splits + 1, C, sfx_c};
+    }
+  }
   // one wave of CTAs when that still cuts the prefix at least in two (GQA models); with many KV heads
   // (MHA: Phi-3 has 32) the prefix CTAs alone fill the wave and the short per-opponent suffix CTAs trail
   const int slots_left = std::max(groups, num_sms(device) - b * n_kv_heads);
@@ -965,12 +1092,14 @@ Attn2Plan plan_attn2_shape(int b, int n_heads, int n_kv_heads, int prefix_len, i
   if (n_splits < 2) n_splits = std::max(1, num_sms(device) / std::max(1, groups));
   n_splits = std::min(n_splits, std::max(1, prefix_len / g_attn_min_split));
   n_splits = std::min(n_splits, 300);
-  return Attn2Plan{opg, n_og, n_splits, groups * (n_splits + opg), n_splits + 1};
+  return Attn2Plan{opg, n_og, n_splits, groups * (n_splits + opg), n_splits + 1, 0, opg};
 }
 void plan_attn2(advspec_engine* e, const std::vector<int>& slots) {
   const auto& d = e->d;
   const int b = (int)slots.size();
-  const Attn2Plan pl = plan_attn2_shape(b, d.n_heads, d.n_kv_heads, e->prefix_len, e->device);
+  const Attn2Plan pl = plan_attn2_shape(b, d.n_heads, d.n_kv_heads, d.head_dim, e->prefix_len, e->device);
+  e->a2_cluster = pl.cluster;
+  e->a2_sfx = pl.sfx;
   e->a2_opg = pl.opg;
   e->a2_n_og = pl.n_og;
   e->a2_n_splits = pl.n_splits;
@@ -1058,8 +1187,9 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       a2.part_m = e->part_m;
       a2.part_l = e->part_l;
       a2.part_o = e->part_o;
-      a2.arrive = e->attn_arrive;
       a2.out = e->dattn;
+      a2.csize = e->a2_cluster;
+      a2.sfx_slots = e->a2_sfx;
       a2.b = b;
       a2.H = d.n_heads;
       a2.Hkv = d.n_kv_heads;
@@ -1072,7 +1202,15 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       a2.dh = d.head_dim;
       E_CUDA(e, launch_attn_decode2(a2, e->a2_ctas, d.head_dim, e->stream, true));
       ADV_TRACE(e->stream, "attn_decode_mma");
-      e->launches -= 2;  // ONE kernel (RoPE + append + attention + last-arriver merge) instead of the 3 counted below
+      if (e->a2_cluster == 0) {
+        E_CUDA(e, launch_pdl(attn_decode_combine2_kernel, dim3(b * d.n_heads), dim3(128), 0, e->stream, true,
+                             (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o, e->dattn,
+                             e->n_slots, d.head_dim));
+        ADV_TRACE(e->stream, "attn_combine2");
+        e->launches -= 1;  // attention + combine instead of the rope + attention + combine counted below
+      } else {
+        e->launches -= 2;  // ONE kernel: RoPE + append + attention + merge of the splits inside the cluster
+      }
     } else {
     E_CUDA(e, launch_pdl(rope_decode_kernel, dim3(b), dim3(256), 0, e->stream, true,
                            (const __nv_bfloat16*)e->dqkv, e->dq, suffix_k(e, l), suffix_v(e, l),
@@ -1112,7 +1250,7 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       chain_plan(&cp, b, &xs, &stg);
       E_CUDA(e, launch_chain(cp, b, xs, stg, e->device, e->stream, true));
       ADV_TRACE(e->stream, "gemv chain");
-      e->launches += 4;  // with the -2 above: attention + chain = 2 launches per layer
+      e->launches += 4;  // attention (+ combine) + chain
       continue;
     }
     GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, tp_resadd_epi(e), d.act, d.norm_eps};
@@ -1317,9 +1455,14 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   g_gemv_impl = gi ? std::max(1, std::min(3, atoi(gi))) : 3;
   const char* ai = getenv("ADVSPEC_ATTN_IMPL");
   g_attn_impl = (ai && atoi(ai) == 1) ? 1 : 2;
+  g_attn_cluster = (ai && atoi(ai) == 3) ? 0 : 1;
   const char* xm = getenv("ADVSPEC_X_SMEM_MAX");
   g_x_smem_max = xm ? (size_t)atoll(xm) : 40000;
   g_gemm_narrow = getenv("ADVSPEC_GEMM_NARROW") != nullptr;
+  const char* gb = getenv("ADVSPEC_GEMM_BAND_MB");
+  g_gemm_band_mb = gb ? std::max(0, atoi(gb)) : 48;
+  const char* gs = getenv("ADVSPEC_GEMM_SPLITK");
+  g_gemm_splitk = gs ? atoi(gs) != 0 : 1;
   const char* tc = getenv("ADVSPEC_ATTN_PREFILL_TC");
   g_attn_prefill_tc = tc ? atoi(tc) != 0 : true;
   const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT");
@@ -1381,8 +1524,8 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, dmalloc(&e->part_o, B * d.n_heads * (size_t)(max_splits + 1) * d.head_dim));
     e->items_cap = d.n_kv_heads * (((int)B * G + 3) / 4) * max_splits + (int)B * d.n_kv_heads * ((G + 3) / 4);
     E_CUDA(e, dmalloc(&e->items, (size_t)e->items_cap));
-    E_CUDA(e, dmalloc(&e->attn_arrive, B * (size_t)d.n_kv_heads));
-    E_CUDA(e, cudaMemsetAsync(e->attn_arrive, 0, B * (size_t)d.n_kv_heads * sizeof(unsigned int), e->stream));
+    E_CUDA(e, dmalloc(&e->gemm_sem, kGemmSemWords));
+    E_CUDA(e, cudaMemsetAsync(e->gemm_sem, 0, kGemmSemWords * sizeof(unsigned int), e->stream));
     E_CUDA(e, dmalloc(&e->chain_bar, 4));
     E_CUDA(e, cudaMemsetAsync(e->chain_bar, 0, 4 * sizeof(unsigned int), e->stream));
     E_CUDA(e, dmalloc(&e->s_pos, B));
@@ -1850,7 +1993,7 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
     key.push_back(e->prefix_gen);
     { int tbits; memcpy(&tbits, &temperature, sizeof tbits); key.push_back(tbits); }
     key.push_back(eos_id);
-    const int64_t per_step = (e->attn_fused ? 5 : 7) * (int64_t)d.n_layers + 3;
+    const int64_t per_step = (e->attn_fused ? (e->a2_cluster ? 5 : 6) : 7) * (int64_t)d.n_layers + 3;
     if (e->use_graph) {
       if (!e->graph || e->graph_key != key) {
         if (e->graph) {
@@ -2141,12 +2284,24 @@ advspec_status advspec_op_gemm(int32_t device, const void* A, int64_t lda, const
   if (s) return s;
   GemmParams p{C, ldc, reinterpret_cast<const float*>(aux), M, N, K, act};
   std::string why;
-  cudaError_t r = launch_gemm(A, lda, M, B, ldb, p, epilogue, device, 0, &why);
+  {  // the A/B knobs are re-read per call (unset = default)
+    const char* gb = getenv("ADVSPEC_GEMM_BAND_MB");
+    g_gemm_band_mb = gb ? std::max(0, atoi(gb)) : 48;
+    const char* gs = getenv("ADVSPEC_GEMM_SPLITK");
+    g_gemm_splitk = gs ? atoi(gs) != 0 : 1;
+  }
+  unsigned int* sem = nullptr;
+  if (cudaMalloc(reinterpret_cast<void**>(&sem), kGemmSemWords * sizeof(unsigned int)) != cudaSuccess) return ADVSPEC_ERR_OOM;
+  cudaMemset(sem, 0, kGemmSemWords * sizeof(unsigned int));
+  cudaError_t r = launch_gemm(A, lda, M, B, ldb, p, epilogue, device, 0, &why, sem);
   if (r != cudaSuccess) {
+    cudaFree(sem);
     g_create_error = std::string("op_gemm launch: ") + cudaGetErrorString(r) + " " + why;
     return ADVSPEC_ERR_CUDA;
   }
-  return op_end("op_gemm");
+  s = op_end("op_gemm");
+  cudaFree(sem);
+  return s;
 }
 
 advspec_status advspec_op_gemm_check(int32_t device, const void* A, int64_t lda, const void* B, int64_t ldb,
@@ -2238,7 +2393,11 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
       return ADVSPEC_ERR_INVALID;
     }
   if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
-  const Attn2Plan pl = plan_attn2_shape(b, n_heads, n_kv_heads, prefix_len, device);
+  {
+    const char* ai = getenv("ADVSPEC_ATTN_IMPL");
+    g_attn_cluster = (ai && atoi(ai) == 3) ? 0 : 1;
+  }
+  const Attn2Plan pl = plan_attn2_shape(b, n_heads, n_kv_heads, head_dim, prefix_len, device);
   CUtensorMap hm[2];
   const int64_t rows = (int64_t)n_kv_heads * prefix_stride;
   if (!make_tmap(&hm[0], prefix_k, rows, head_dim, head_dim, 64) ||
@@ -2249,19 +2408,16 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
   CUtensorMap* dmaps = nullptr;
   int* dpos = nullptr;
   float *pm = nullptr, *plv = nullptr, *po = nullptr;
-  unsigned int* arr = nullptr;
   const size_t nrow = (size_t)b * n_heads * pl.n_slots;
   auto cleanup = [&]() {
     cudaFree(dmaps);
     cudaFree(dpos);
-    cudaFree(arr);
     cudaFree(pm);
     cudaFree(plv);
     cudaFree(po);
   };
   if (cudaMalloc(reinterpret_cast<void**>(&dmaps), sizeof hm) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&dpos), 8 * sizeof(int)) != cudaSuccess ||
-      cudaMalloc(reinterpret_cast<void**>(&arr), (size_t)b * n_kv_heads * sizeof(unsigned int)) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&pm), nrow * 4) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&plv), nrow * 4) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&po), nrow * head_dim * 4) != cudaSuccess) {
@@ -2271,7 +2427,6 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
   }
   cudaMemcpy(dmaps, hm, sizeof hm, cudaMemcpyHostToDevice);
   cudaMemcpy(dpos, pos_host, b * sizeof(int), cudaMemcpyHostToDevice);
-  cudaMemset(arr, 0, (size_t)b * n_kv_heads * sizeof(unsigned int));
   AttnDecode2Params a2{};
   a2.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
   a2.rope_cos = reinterpret_cast<const float*>(rope_cos);
@@ -2289,8 +2444,9 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
   a2.part_m = pm;
   a2.part_l = plv;
   a2.part_o = po;
-  a2.arrive = arr;
   a2.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a2.csize = pl.cluster;
+  a2.sfx_slots = pl.sfx;
   a2.b = b;
   a2.H = n_heads;
   a2.Hkv = n_kv_heads;
@@ -2302,11 +2458,10 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
   a2.scale = 1.0f / sqrtf((float)head_dim);
   a2.dh = head_dim;
   cudaError_t r = launch_attn_decode2(a2, pl.ctas, head_dim, 0, false);
-  if (r == cudaSuccess) {
-    // run it twice: the second launch appends the same row again and must find the arrival counters reset
-    cudaMemset(out, 0xff, (size_t)b * n_heads * head_dim * 2);
-    r = launch_attn_decode2(a2, pl.ctas, head_dim, 0, false);
-  }
+  if (r == cudaSuccess && pl.cluster == 0)
+    r = launch_pdl(attn_decode_combine2_kernel, dim3(b * n_heads), dim3(128), 0, (cudaStream_t)0, false,
+                   (const float*)pm, (const float*)plv, (const float*)po, reinterpret_cast<__nv_bfloat16*>(out),
+                   pl.n_slots, (int)head_dim);
   if (r != cudaSuccess) {
     cleanup();
     g_create_error = std::string("op_attn_decode launch: ") + cudaGetErrorString(r);

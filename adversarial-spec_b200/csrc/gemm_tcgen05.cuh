@@ -8,8 +8,13 @@
 //   warp 2           TMEM allocate / free
 //   warps 4..7       epilogue: tcgen05.ld -> registers -> fused op -> global
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of
-// tile i+1.  Roofline: tensor pipe (2*M*N*K flops); operand traffic is L2-served
-// after the first touch because tiles are walked M-fastest.
+// tile i+1.  Roofline: tensor pipe (2*M*N*K flops).
+// Tile order (GemmSched): M-fastest inside BANDS of m-tiles sized so that a band of A stays in L2 while
+// the weight tiles stream past it once per band (the 5,068 x 14,336 down-proj input is 147 MB: walked
+// M-fastest over all 40 m-tiles it was re-read from DRAM every wave — 963 MB of reads for 345 MB).
+// fp32 epilogues (residual add / plain store) may split the tiles of the last, partial wave along K
+// among the SMs that would otherwise idle; the splits of a tile add into C in split order (a per-tile
+// semaphore), so the result does not depend on timing.
 #pragma once
 
 #include "common.cuh"
@@ -33,17 +38,53 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return act == ACT_GELU_TANH ? act_gelu_tanh(x) : act_silu(x);
 }
 
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int kGemmThreads = 256;
+
 struct GemmParams {
   void* C;
   int64_t ldc;        // elements of C's row pitch
   const float* bias;  // EPI_BF16 only, may be null
   int M, N, K;
   int act;
+  // schedule (filled by the host launcher, see gemm_schedule in engine.cu)
+  int band_m;         // m-tiles per raster band (>= 1)
+  int full_items;     // work items [0, full_items) are whole tiles
+  int split;          // tiles past full_items are cut into `split` K-ranges each (1 = none)
+  int total_items;    // full_items + (tiles - full_items) * split
+  unsigned int* sem;  // [tiles - full_items] zero-initialised ordering words (split > 1 only)
 };
 
-constexpr int kGemmBM = 128;
-constexpr int kGemmBK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int kGemmThreads = 256;
+// One work item of the persistent loop: an output tile and the K-blocks [kb0, kb1) it accumulates.
+struct GemmWork {
+  int m0, n0, kb0, kb1, q, tail_idx;
+};
+template <int BN>
+__device__ __forceinline__ GemmWork gemm_work(const GemmParams& p, int w, int num_m, int num_n, int num_kb) {
+  GemmWork r;
+  int t;
+  if (w < p.full_items) {
+    t = w;
+    r.q = 0;
+    r.kb0 = 0;
+    r.kb1 = num_kb;
+    r.tail_idx = -1;
+  } else {
+    const int rr = w - p.full_items;
+    r.tail_idx = rr / p.split;
+    r.q = rr % p.split;
+    t = p.full_items + r.tail_idx;
+    r.kb0 = (int)((int64_t)num_kb * r.q / p.split);
+    r.kb1 = (int)((int64_t)num_kb * (r.q + 1) / p.split);
+  }
+  const int per_band = p.band_m * num_n;
+  const int b = t / per_band, within = t - b * per_band;
+  const int h = min(p.band_m, num_m - b * p.band_m);
+  r.m0 = (b * p.band_m + within % h) * kGemmBM;
+  r.n0 = (within / h) * BN;
+  return r;
+}
 
 template <int BN>
 struct GemmCfg {
@@ -80,7 +121,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int num_m = (p.M + kGemmBM - 1) / kGemmBM;
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + kGemmBK - 1) / kGemmBK;
 
   if (warp == 0 && lane == 0) {
@@ -111,14 +151,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ TMA producer ------------------------------
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t % num_m) * kGemmBM;
-      const int n0 = (t / num_m) * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      const GemmWork wk = gemm_work<BN>(p, w, num_m, num_n, num_kb);
+      for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u, 0x100u + stage);
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-        tma_load_2d(smemA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kGemmBK, m0);
-        tma_load_2d(smemB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kGemmBK, n0);
+        tma_load_2d(smemA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kGemmBK, wk.m0);
+        tma_load_2d(smemB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kGemmBK, wk.n0);
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -128,13 +167,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++iter) {
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++iter) {
+      const GemmWork wk = gemm_work<BN>(p, w, num_m, num_n, num_kb);
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 0x200u + acc);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase, 0x300u + stage);
         tc_fence_after();
         const uint64_t da = make_smem_desc_sw128(smem_u32(smemA + stage * Cfg::kABytes));
@@ -143,10 +183,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int k = 0; k < kGemmBK / 16; ++k) {
           // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
           tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                     (kb | k) != 0 ? 1u : 0u);
+                     (kb != wk.kb0 || k != 0) ? 1u : 0u);
         }
         tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-        if (kb == num_kb - 1) tc_commit(&tfull_bar[acc]);
+        if (kb == wk.kb1 - 1) tc_commit(&tfull_bar[acc]);
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -154,13 +194,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ epilogue ----------------------------------
     const int quad = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
     int iter = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++iter) {
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++iter) {
+      const GemmWork wk = gemm_work<BN>(p, w, num_m, num_n, num_kb);
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      const int m0 = (t % num_m) * kGemmBM;
-      const int n0 = (t / num_m) * BN;
+      const int m0 = wk.m0, n0 = wk.n0;
       mbar_wait(&tfull_bar[acc], acc_phase, 0x400u + acc);
       tc_fence_after();
+      // K-split tail tile: the splits add into C in split order (deterministic sums)
+      bool add_into = (EPI == EPI_RESADD_F32);
+      if constexpr (EPI == EPI_RESADD_F32 || EPI == EPI_F32) {
+        if (wk.tail_idx >= 0 && p.split > 1) {
+          if (wk.q > 0) {
+            add_into = true;
+            if (lane == 0) {
+              const uint64_t t0 = global_timer_ns();
+              while (*(volatile unsigned int*)&p.sem[wk.tail_idx] != (unsigned int)wk.q) {
+                if (*(volatile unsigned int*)&g_watchdog_code != 0) break;
+                if (global_timer_ns() - t0 > 2000000000ull) {
+                  atomicCAS(&g_watchdog_code, 0u, 0x80000000u | 0x500u);
+                  break;
+                }
+              }
+            }
+            __syncwarp();
+            __threadfence();  // acquire the earlier splits' stores
+          }
+        }
+      }
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
@@ -200,8 +261,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 o;
-              if constexpr (EPI == EPI_RESADD_F32) {
-                o = *reinterpret_cast<const float4*>(out + j);
+              if (add_into) {
+                o = __ldcg(reinterpret_cast<const float4*>(out + j));
               } else {
                 o = make_float4(0.f, 0.f, 0.f, 0.f);
               }
@@ -213,7 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
             for (int j = 0; j < 32 && n + j < p.N; ++j) {
-              const float base = (EPI == EPI_RESADD_F32) ? out[j] : 0.f;
+              const float base = add_into ? __ldcg(out + j) : 0.f;
               out[j] = base + __uint_as_float(v[j]);
             }
           }
@@ -242,6 +303,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // all of this thread's TMEM reads for the tile are complete (tmem_ld_wait above)
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
+      if constexpr (EPI == EPI_RESADD_F32 || EPI == EPI_F32) {
+        if (wk.tail_idx >= 0 && p.split > 1) {
+          // the four epilogue warps own disjoint rows of the tile: each publishes its rows, the last of
+          // the four (named barrier) hands the tile to the next split, the final split re-zeroes the word
+          __threadfence();
+          named_bar_sync(1, 128);
+          if (warp == 4 && lane == 0) {
+            __threadfence();
+            *(volatile unsigned int*)&p.sem[wk.tail_idx] = (wk.q + 1 == p.split) ? 0u : (unsigned int)(wk.q + 1);
+          }
+        }
+      }
     }
   }
 

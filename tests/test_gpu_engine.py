@@ -285,10 +285,11 @@ def test_eos_stops_one_opponent_only(cuda_device):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [{"ADVSPEC_CHAIN": "1"}, {"ADVSPEC_L2_EVICT_FIRST": "0"}, {"ADVSPEC_NO_PDL": "1"},
-                                 {"ADVSPEC_ATTN_IMPL": "1"}])
+                                 {"ADVSPEC_ATTN_IMPL": "1"}, {"ADVSPEC_ATTN_IMPL": "3"}])
 def test_opt_in_decode_variants_give_the_default_logits(cuda_device, diag, monkeypatch, env):
     """The A/B knobs of DESIGN.md §4 (persistent GEMV chain, L2 policy, no programmatic launch, the
-    scalar decode attention) change scheduling, not arithmetic: teacher-forced decode logits must match
+    scalar decode attention, the split + combine-kernel attention instead of the cluster merge) change
+    scheduling, not arithmetic: teacher-forced decode logits must match
     the default path within the HF tolerance, and exactly where the kernels are the same."""
     rng = np.random.default_rng(21)
 

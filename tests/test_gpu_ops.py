@@ -34,8 +34,10 @@ def _gemm_ref(A, B, epi, act, bias, Cin):
     return acc
 
 
+# the last two are the benchmark's own o-proj and down-proj (5,068 prompt rows): 640 tiles = 4.3 waves of 148,
+# so the fp32 epilogues cut the last wave's 48 tiles three ways along K, and K = 14,336 walks A in 3 bands
 GEMM_SHAPES = [(128, 256, 64), (256, 512, 512), (384, 768, 320), (200, 1000, 264), (70, 128, 128),
-               (1024, 6144, 4096)]
+               (1024, 6144, 4096), (5068, 4096, 4096), (5068, 4096, 14336)]
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
@@ -106,6 +108,39 @@ def test_gemv(cuda_device, diag, N, K, b, mode):
     e = float((y.float() - ref.float()).abs().max()) / scale
     diag[f"gemv/{N}x{K}/b{b}/in{in_mode}/epi{epi}"] = e
     assert e < (1e-2 if epi in (0, 2) else 2e-3), e
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(5068, 4096, 14336, 1), (5068, 4096, 4096, 3), (2100, 3584, 18944, 1),
+                                       (9000, 8192, 3584, 1)])
+def test_gemm_k_split_tail_is_deterministic_and_schedule_independent(cuda_device, diag, monkeypatch, M, N, K, epi):
+    """The K-split of the last partial wave adds its partial tiles in split order: two runs give the same
+    bits, and the result differs from the unsplit, single-band schedule only by fp32 summation order."""
+    lib = eng.load_library()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    C0 = torch.randn(M, N, device="cuda", generator=g)
+
+    def run():
+        Cb = C0.clone()
+        st = lib.advspec_op_gemm(0, _ptr(A), K, _ptr(B), K, _ptr(Cb), N, None, M, N, K, epi, 0)
+        assert st == 0, _err(lib)
+        return Cb
+
+    a, b = run(), run()
+    assert torch.equal(a, b), "same schedule, same bits"
+    monkeypatch.setenv("ADVSPEC_GEMM_SPLITK", "0")
+    monkeypatch.setenv("ADVSPEC_GEMM_BAND_MB", "0")
+    plain = run()
+    monkeypatch.delenv("ADVSPEC_GEMM_SPLITK")
+    monkeypatch.delenv("ADVSPEC_GEMM_BAND_MB")
+    run()  # restores the defaults inside the library (the knobs are re-read per call)
+    ref = A.float() @ B.float().T + (C0 if epi == 1 else 0)
+    scale = float(ref.abs().max())
+    e_split, e_plain = float((a - ref).abs().max()) / scale, float((plain - ref).abs().max()) / scale
+    diag[f"gemm_ksplit/{M}x{N}x{K}/epi{epi}"] = {"split_rel_err": e_split, "plain_rel_err": e_plain,
+                                                 "split_vs_plain": float((a - plain).abs().max()) / scale}
+    assert e_split < 2e-3 and e_plain < 2e-3, (e_split, e_plain)
 
 
 def _attn_ref(q, kc, vc, n_q, q_pos0, H, Hkv, Dh):
