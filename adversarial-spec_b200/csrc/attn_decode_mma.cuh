@@ -1,15 +1,7 @@
 // attn_decode_mma.cuh — decode attention, second design: one kernel per layer does
 //   RoPE of the new q/k  ->  append k/v to the opponent's private suffix KV
 //   ->  split-KV flash-decoding on tensor cores (mma.sync m16n8k16, bf16)
-//   ->  per-split partial (m, l, o).  Two ways to merge the splits:
-//       CL = true : the CTAs of one (KV head, opponent group) — its prefix splits and its suffix items —
-//                   are ONE thread-block cluster; each leaves its (m, l, o) in shared memory and, after a
-//                   cluster barrier, every CTA merges its slice of the head dimensions from its peers'
-//                   shared memory (DSMEM) and writes the bf16 attention output.  No partials in global
-//                   memory, no second kernel.
-//       CL = false: partials go to global memory and attn_decode_combine2_kernel (below) merges them —
-//                   for shapes whose groups do not map onto clusters of 8 or 16 CTAs (one KV head per
-//                   tensor-parallel rank: 147 splits; 32 MHA heads: more groups than clusters fit).
+//   ->  per-split partial (m, l, o); attn_decode_combine2_kernel (below) merges the splits.
 // A work item is (KV head, opponent group, KV source): the shared prefix is cut
 // into splits that are read ONCE for all opponents and all query heads of the KV
 // head (up to 16 query rows = one MMA M tile); each opponent's suffix is its own
@@ -19,8 +11,6 @@
 // Head dims 64 / 128 / 256 natively, 96 in the 128-wide tile with zero padding.
 // Replaces rope_decode_kernel + attn_decode_kernel + attn_decode_combine_kernel.
 #pragma once
-
-#include <cooperative_groups.h>
 
 #include "attn.cuh"
 #include "common.cuh"
@@ -45,19 +35,16 @@ struct AttnDecode2Params {
   const int* pos_b;          // [b] absolute position of each opponent's new token (device state)
   int slots[8];              // batch index -> opponent slot (fixed for the decode call)
   int prefix_len;
-  float* part_m;             // [b*H][n_slots]                  (CL = false)
+  float* part_m;             // [b*H][n_slots]
   float* part_l;
   float* part_o;             // [b*H][n_slots][DH]
-  __nv_bfloat16* out;        // [b][H*dh] attention output    (CL = true)
-  int csize;                 // cluster size = n_splits + sfx_slots (CL = true)
-  int sfx_slots;             // suffix items per group in the grid (CL = false: opg; CL = true: min(opg, b))
   int b, H, Hkv, G;
   int opg, n_og, n_splits, n_slots;  // opponents per group, groups per KV head, prefix splits, n_splits+1
   float scale;
   int dh;                    // head_dim in GLOBAL memory (<= DH): Phi-3's 96 runs in the 128-wide tile, zero-padded
 };
 
-template <int DH, int NST, bool CL>
+template <int DH, int NST>
 __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Params p) {
   constexpr int BN = 64;
   constexpr int CPR = DH / 8;
@@ -92,32 +79,30 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
   // suffix CTAs backfill behind them, instead of a second wave that again contains full-length prefix CTAs.
   const int n_prefix = p.Hkv * p.n_og * p.n_splits;
   int grp, j;
-  if constexpr (CL) {  // a cluster = the items of one group: rank j < n_splits is a prefix split, the rest suffix items
-    grp = blockIdx.x / p.csize;
-    j = blockIdx.x % p.csize;
-  } else if ((int)blockIdx.x < n_prefix) {
+  if ((int)blockIdx.x < n_prefix) {
     grp = blockIdx.x / p.n_splits;
     j = blockIdx.x % p.n_splits;
   } else {
     const int r = blockIdx.x - n_prefix;
-    grp = r / p.sfx_slots;
-    j = p.n_splits + r % p.sfx_slots;
+    grp = r / p.opg;
+    j = p.n_splits + r % p.opg;
   }
   const int hk = grp / p.n_og, og = grp % p.n_og;
   const int o0 = og * p.opg;
   const int n_opp = min(p.opg, p.b - o0);
   const bool is_prefix = j < p.n_splits;
-  // padding item of a short last group: nothing to do — but a cluster member must still meet its peers at the
-  // cluster barriers, so it runs through with an empty key range
-  const bool idle = !is_prefix && (j - p.n_splits) >= n_opp;
-  if (!CL && idle) return;
+  if (!is_prefix && (j - p.n_splits) >= n_opp) return;  // padding item of a short last group
   const int row_off = is_prefix ? 0 : (j - p.n_splits) * p.G;  // rows inside the group's 16-row tile
-  const int n_rows = idle ? 0 : (is_prefix ? n_opp * p.G : p.G);
+  const int n_rows = is_prefix ? n_opp * p.G : p.G;
   const int slot_out = is_prefix ? j : p.n_splits;
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) mbar_init(&full_bar[s], 1);
     fence_mbar_init();
+  }
+  if (tid == 32) {  // the K/V tensor maps live in global memory: start fetching them before the first TMA needs them
+    tma_prefetch_desc(&p.maps[0]);
+    tma_prefetch_desc(&p.maps[1]);
   }
   __syncthreads();
 
@@ -128,12 +113,6 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     vb = p.pv + (int64_t)hk * p.pstride * dhg;
     tb = (int)((int64_t)p.prefix_len * j / p.n_splits);
     te = (int)((int64_t)p.prefix_len * (j + 1) / p.n_splits);
-  } else if (idle) {
-    pdl_wait();
-    kb = p.sk;
-    vb = p.sv;
-    tb = 0;
-    te = 0;
   } else {
     pdl_wait();  // needs this step's projections and positions
     // append the new token's k (rotated) and v to this opponent's suffix, then attend over it
@@ -265,6 +244,7 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
       cp_async_wait<NST - 1>();
       __syncthreads();
     }
+    phase_mark(6 + (jt < 9 ? jt : 9));  // tile jt's data has landed (diagnostic stamps 6..15)
     if ((jt & 1) == wg) {
       const __nv_bfloat16* bK = sKV + (size_t)(jt % NST) * 2 * TILE;
       const __nv_bfloat16* bV = bK + TILE;
@@ -381,73 +361,21 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     s_ML[2 * tid + 1] = L;
   }
   __syncthreads();
-  if constexpr (!CL) {
-    for (int idx = tid; idx < n_rows * dhg; idx += 256) {
-      const int r = idx / dhg, d = idx % dhg;
-      float O = 0.f;
+  for (int idx = tid; idx < n_rows * dhg; idx += 256) {
+    const int r = idx / dhg, d = idx % dhg;
+    float O = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) O += s_o[(w * 16 + r) * OP + d] * s_c[w * 16 + r];
-      const int gr = row_off + r;
-      const int bi = o0 + gr / p.G, head = hk * p.G + gr % p.G;
-      const int64_t ps = ((int64_t)bi * p.H + head) * p.n_slots + slot_out;
-      p.part_o[ps * dhg + d] = O;
-      if (d == 0) {
-        p.part_m[ps] = s_ML[2 * r];
-        p.part_l[ps] = s_ML[2 * r + 1];
-      }
+    for (int w = 0; w < 8; ++w) O += s_o[(w * 16 + r) * OP + d] * s_c[w * 16 + r];
+    const int gr = row_off + r;
+    const int bi = o0 + gr / p.G, head = hk * p.G + gr % p.G;
+    const int64_t ps = ((int64_t)bi * p.H + head) * p.n_slots + slot_out;
+    p.part_o[ps * dhg + d] = O;
+    if (d == 0) {
+      p.part_m[ps] = s_ML[2 * r];
+      p.part_l[ps] = s_ML[2 * r + 1];
     }
-  } else {
-    // ---- cluster merge through distributed shared memory
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    float* c_ML = s_ML + 32;       // [16][2]  this CTA's merged (M, L) per local row (M = -inf: no keys)
-    float* c_O = c_ML + 32;        // [16][DH] this CTA's merged, un-normalised output rows
-    for (int idx = tid; idx < 16 * DH; idx += 256) {
-      const int r = idx / DH, d = idx % DH;
-      float O = 0.f;
-      if (r < n_rows) {
-#pragma unroll
-        for (int w = 0; w < 8; ++w) O += s_o[(w * 16 + r) * OP + d] * s_c[w * 16 + r];
-      }
-      c_O[idx] = O;
-    }
-    if (tid < 16) {
-      c_ML[2 * tid] = tid < n_rows ? s_ML[2 * tid] : -INFINITY;
-      c_ML[2 * tid + 1] = tid < n_rows ? s_ML[2 * tid + 1] : 0.f;
-    }
-    cluster.sync();  // every member's (M, L, O) is in its shared memory
-    phase_mark(5);
-    // this CTA merges head dimensions [j * DH / csize, (j + 1) * DH / csize) of every row of the group
-    const int dpc = DH / p.csize;
-    const int g_rows = n_opp * p.G;
-    for (int idx = tid; idx < g_rows * dpc; idx += 256) {
-      const int gr = idx / dpc, d = j * dpc + idx % dpc;
-      const int sfx_rank = p.n_splits + gr / p.G, sfx_row = gr % p.G;
-      float M = -INFINITY;
-      for (int c = 0; c <= p.n_splits; ++c) {
-        const int rank = c < p.n_splits ? c : sfx_rank;
-        const float* pml = cluster.map_shared_rank(c_ML, rank);
-        M = fmaxf(M, pml[2 * (c < p.n_splits ? gr : sfx_row)]);
-      }
-      float L = 0.f, O = 0.f;
-      for (int c = 0; c <= p.n_splits; ++c) {
-        const int rank = c < p.n_splits ? c : sfx_rank;
-        const int lr = c < p.n_splits ? gr : sfx_row;
-        const float* pml = cluster.map_shared_rank(c_ML, rank);
-        const float* po = cluster.map_shared_rank(c_O, rank);
-        const float mc = pml[2 * lr];
-        const float wc = (mc == -INFINITY) ? 0.f : exp2f(mc - M);
-        L = fmaf(pml[2 * lr + 1], wc, L);
-        O = fmaf(po[lr * DH + d], wc, O);
-      }
-      if (d < dhg) {
-        const int bi = o0 + gr / p.G, head = hk * p.G + gr % p.G;
-        p.out[((int64_t)bi * p.H + head) * dhg + d] = __float2bfloat16_rn(L > 0.f ? O / L : 0.f);
-      }
-    }
-    cluster.sync();  // nobody leaves while a peer still reads its shared memory
   }
-  phase_mark(6);
+  phase_mark(5);
   pdl_launch_dependents();
 }
 

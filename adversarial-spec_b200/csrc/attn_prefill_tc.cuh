@@ -2,15 +2,20 @@
 //
 // One CTA = 128 query rows of one head; keys in tiles of 128.  Per tile
 //   S = Q K^T   tcgen05.mma 128x128x128, Q and K K-major from TMA-swizzled shared memory, S in TMEM
-//   softmax     8 warps, TWO THREADS PER QUERY ROW (64 keys each; the exponentials are MUFU-bound, so the
-//               row is split): tcgen05.ld the scores, mask, exp2 against a
-//               lazily-updated row maximum (rescale O only when the maximum grew by > 2^8), write P
-//               (bf16) back to shared memory in the 128B-swizzled K-major layout
+//   softmax     8 warps, TWO THREADS PER QUERY ROW (64 keys each): tcgen05.ld the scores, mask, exp2 against
+//               a lazily-updated row maximum (rescale O only when the maximum grew by > 2^8), write P
+//               (bf16) back to shared memory in the 128B-swizzled K-major layout.  The exponentials were
+//               the limiter (16,384 MUFU.EX2 per tile = the tile's MMA time): every other 8-key chunk now
+//               takes a degree-3 polynomial on the FMA pipe instead (relative error 1e-4, P is rounded to
+//               bf16 = 4e-3 anyway), and P is DOUBLE-BUFFERED so the softmax of tile j+1 runs under the
+//               P V of tile j instead of waiting for it
 //   O += P V    tcgen05.mma 128x128x128, A = P (K-major), B = V straight from its [key][dim] tile as an
 //               MN-major operand; O accumulates in TMEM across all tiles
 // Warp roles: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-9 softmax/epilogue.
 // S is double-buffered in TMEM so QK^T of tile j+1 runs under the softmax of tile j.
 // TMEM columns: S0 [0,128) S1 [128,256) O [256,384).  head_dim 128 only (64/96/256 use attn.cuh).
+// Shared memory: Q, P x2, (K, V) x2 stages = 7 x 32 KB + barriers + the row-maximum exchange = the whole
+// 227 KB of the SM.
 #pragma once
 
 #include "attn.cuh"
@@ -22,7 +27,11 @@ constexpr int kAtBM = 128, kAtBN = 128, kAtDH = 128;
 constexpr int kAtStages = 2;
 constexpr int kAtHalf = 128 * 64 * 2;               // bytes of a [128 rows][64 elems] half tile (16 KB)
 constexpr int kAtTile = 2 * kAtHalf;                // 32 KB: Q, K, V or P tile
-constexpr int kAtSmem = kAtTile * (2 + 2 * kAtStages) + 256 + 1024;  // Q, P, K/V stages, barriers, alignment
+constexpr int kAtBarBytes = 128;
+constexpr int kAtMxBytes = 2 * 2 * 128 * 4;         // [tile parity][column half][row] row-maximum exchange
+// Q, P x2, K/V stages, barriers, exchange, alignment slack (the base is 128-byte aligned: at most 896 bytes)
+constexpr int kAtSmem = kAtTile * (3 + 2 * kAtStages) + kAtBarBytes + kAtMxBytes + 896;
+static_assert(kAtSmem <= 232448, "the prompt-attention CTA needs the whole 227 KB");
 constexpr int kAtThreads = 320;  // TMA warp, MMA warp, 8 softmax warps (2 threads per query row)
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -51,6 +60,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, 
   return d;
 }
 
+// 2^x on the FMA pipe: x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 polynomial
+// (max relative error 1.0e-4), 2^n by adding n to the exponent field.  x is clamped at -126 (a masked
+// score of -inf becomes 1e-38, nothing in a sum of O(1) terms).
+__device__ __forceinline__ float exp2_poly3(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the low mantissa bits now hold round(x)
+  const float f = x - (t - 12582912.0f);
+  const float p = fmaf(f, fmaf(f, fmaf(f, 0.05500892922282219f, 0.24221095442771912f), 0.6932829022407532f), 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 struct AttnPrefillTcParams {
   __nv_bfloat16* out;  // [n_q][H*128]
   int n_q, q_pos0, H, Hkv;
@@ -63,23 +83,24 @@ struct AttnPrefillTcParams {
 __global__ void __launch_bounds__(kAtThreads, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, AttnPrefillTcParams p) {
-  extern __shared__ uint8_t at_raw[];
+  extern __shared__ __align__(128) uint8_t at_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
-  uint8_t* sP = smem + kAtTile;
-  uint8_t* sK = smem + 2 * kAtTile;                     // [stages]
-  uint8_t* sV = smem + (2 + kAtStages) * kAtTile;       // [stages]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + 2 * kAtStages) * kAtTile);
+  uint8_t* sP = smem + kAtTile;                         // [2]: tile parity
+  uint8_t* sK = smem + 3 * kAtTile;                     // [stages]
+  uint8_t* sV = smem + (3 + kAtStages) * kAtTile;       // [stages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (3 + 2 * kAtStages) * kAtTile);
   uint64_t* q_full = bars;                 // 1
   uint64_t* kv_full = bars + 1;            // [stages]
   uint64_t* kv_empty = bars + 1 + kAtStages;  // [stages]
   uint64_t* s_full = bars + 1 + 2 * kAtStages;   // [2]
   uint64_t* s_empty = s_full + 2;          // [2]
-  uint64_t* p_full = s_empty + 2;          // 1
-  uint64_t* pv_done = p_full + 1;          // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
-  __shared__ float s_mx[2][2][128];  // [tile parity][column half][row]: row-maximum exchange between the two threads of a row
-  __shared__ float s_lsum[2][128];
+  uint64_t* p_full = s_empty + 2;          // [2]: P of tile j is in buffer j & 1
+  uint64_t* pv_done = p_full + 2;          // [2]: P V of tile j retired (frees P buffer j & 1 and, in order, O)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  // [tile parity][column half][row]: row-maximum exchange between the two threads of a row (and, after the
+  // last tile, their shares of the row sum)
+  float (*s_mx)[2][128] = reinterpret_cast<float (*)[2][128]>(smem + (3 + 2 * kAtStages) * kAtTile + kAtBarBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qtiles = (p.n_q + kAtBM - 1) / kAtBM;
@@ -104,8 +125,10 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 256);
     }
-    mbar_init(p_full, 256);
-    mbar_init(pv_done, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&p_full[s], 256);
+      mbar_init(&pv_done[s], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -155,17 +178,17 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     issue_qk(0);
     for (int j = 0; j < n_t; ++j) {
       if (j + 1 < n_t) issue_qk(j + 1);
-      const int s = j % kAtStages;
-      mbar_wait(p_full, (uint32_t)j & 1u, 0xA30u);
+      const int s = j % kAtStages, pb = j & 1;
+      mbar_wait(&p_full[pb], ((uint32_t)(j >> 1)) & 1u, 0xA30u + pb);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < kAtBN / 16; ++k) {
         const uint32_t offp = (uint32_t)(k >> 2) * kAtHalf + (uint32_t)(k & 3) * 32u;  // P: K-major over keys
         const uint32_t offv = (uint32_t)k * 16u * 128u;                                 // V: 16 key rows of 128 B
-        tc_mma_f16(tO, make_smem_desc_sw128(smem_u32(sP) + offp),
+        tc_mma_f16(tO, make_smem_desc_sw128(smem_u32(sP + pb * kAtTile) + offp),
                    make_smem_desc_sw128_mn(smem_u32(sV + s * kAtTile) + offv, kAtHalf), idesc_pv, (j | k) != 0 ? 1u : 0u);
       }
-      tc_commit(pv_done);
+      tc_commit(&pv_done[pb]);
       tc_commit(&kv_empty[s]);
     }
   } else if (warp >= 2) {
@@ -204,8 +227,6 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       s_mx[b][ch][row] = mx;
       named_bar_sync(2, 256);
       mx = fmaxf(mx, s_mx[b][ch ^ 1][row]);
-      // P smem and the O accumulator are only touched once the previous tile's P V has retired
-      if (j > 0) mbar_wait(pv_done, ((uint32_t)(j - 1)) & 1u, 0xB10u);
       // lazy rescale: keep exponentiating against m_used until the row maximum has grown by > 2^8
       const bool grow = (mx > m_used + 8.0f / sl2) || (m_used == -INFINITY && mx != -INFINITY);
       if (__any_sync(0xffffffffu, grow)) {
@@ -213,6 +234,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const float corr = (m_used == -INFINITY) ? 0.f : exp2f((m_used - m_new) * sl2);
         l_run *= corr;
         if (j > 0) {
+          // the O accumulator may only be touched once the previous tile's P V has retired
+          mbar_wait(&pv_done[(j - 1) & 1], ((uint32_t)((j - 1) >> 1)) & 1u, 0xB10u);
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -228,14 +251,17 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         m_used = m_new;
       }
       const float m_off = (m_used == -INFINITY) ? 0.f : m_used * sl2;
+      // this tile's P buffer is free once the P V of tile j-2 has retired (it has, except under a long stall)
+      if (j >= 2) mbar_wait(&pv_done[j & 1], ((uint32_t)((j - 2) >> 1)) & 1u, 0xB18u);
       float rs = 0.f;
-      uint8_t* prow = sP + (size_t)ch * kAtHalf + (size_t)row * 128;  // keys [ch*64, ch*64+64) = P half `ch`
+      uint8_t* prow = sP + (size_t)(j & 1) * kAtTile + (size_t)ch * kAtHalf + (size_t)row * 128;  // keys [ch*64, +64)
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {  // 16-byte chunks of 8 keys
+      for (int c8 = 0; c8 < 8; ++c8) {  // 16-byte chunks of 8 keys, alternately on the MUFU and the FMA pipe
         float pv[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          pv[e] = exp2f(__uint_as_float(sv[c8 * 8 + e]) * sl2 - m_off);
+          const float x = __uint_as_float(sv[c8 * 8 + e]) * sl2 - m_off;
+          pv[e] = (c8 & 1) ? exp2_poly3(x) : exp2f(x);
           rs += pv[e];
         }
         uint4 o;
@@ -248,13 +274,14 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       l_run += rs;
       fence_proxy_async();  // P was written by the generic proxy; the MMA reads it through the async proxy
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[j & 1]);
     }
     // ---- epilogue: O / l -> bf16 -> global (two threads share one 256-byte output row)
+    float (*s_lsum)[128] = s_mx[n_t & 1];  // the parity buffer the last tile did not use
     s_lsum[ch][row] = l_run;
     named_bar_sync(2, 256);
     const float l_tot = s_lsum[0][row] + s_lsum[1][row];
-    mbar_wait(pv_done, ((uint32_t)(n_t - 1)) & 1u, 0xB20u);
+    mbar_wait(&pv_done[(n_t - 1) & 1], ((uint32_t)((n_t - 1) >> 1)) & 1u, 0xB20u);
     tc_fence_after();
     const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
     const int qr = q0 + row;

@@ -614,58 +614,33 @@ cudaError_t launch_attn_decode(const AttnDecodeParams& p, int n_items, int DH, c
 
 int g_attn_impl = 2;  // 2: fused tensor-core decode attention (default); 1: scalar 3-kernel path (A/B, other head dims)
 
-// dynamic shared memory of attn_decode_mma_kernel<DH, NST>: query tile + K/V ring + alignment slack + barriers
-int attn2_smem_bytes(int DH) {
-  if (DH == 256) return 16 * 256 * 2 + 3 * 2 * 64 * 256 * 2 + 1024 + 128;
-  if (DH == 64) return 16 * 64 * 2 + 6 * 2 * 64 * 64 * 2 + 1024 + 128;
-  return 16 * 128 * 2 + 6 * 2 * 64 * 128 * 2 + 1024 + 128;
-}
-
-template <int DH, int NST, bool CL>
-cudaError_t launch_attn_decode2_t(const AttnDecode2Params& p, int n_ctas, int smem, cudaStream_t st, bool pdl) {
-  auto kern = attn_decode_mma_kernel<DH, NST, CL>;
-  {  // function attributes are per device: set on every launch (host-side, microseconds)
-    cudaError_t e = set_smem(kern, smem);
-    if (e != cudaSuccess) return e;
-  }
-  if (!CL) return launch_pdl(kern, dim3(n_ctas), dim3(256), smem, st, pdl, p);
-  if (p.csize > 8) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return e;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(n_ctas);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = p.csize;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = (pdl && g_use_pdl) ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, kern, p);
-}
-
 cudaError_t launch_attn_decode2(const AttnDecode2Params& p, int n_ctas, int DH, cudaStream_t st, bool pdl) {
-  const bool cl = p.csize > 0;
+  constexpr int NST = 6;
+  dim3 g(n_ctas), blk(256);
   if (DH == 128 || DH == 96) {  // 96 (Phi-3): the 128-wide tile with zero padding, p.dh = 96
-    const int smem = attn2_smem_bytes(128);
-    return cl ? launch_attn_decode2_t<128, 6, true>(p, n_ctas, smem, st, pdl)
-              : launch_attn_decode2_t<128, 6, false>(p, n_ctas, smem, st, pdl);
+    const int smem = 16 * 128 * 2 + NST * 2 * 64 * 128 * 2 + 1024 + 128;  // + alignment slack + barriers
+    {  // function attributes are per device: set on every launch (host-side, microseconds)
+      cudaError_t e = set_smem(attn_decode_mma_kernel<128, NST>, smem);
+      if (e != cudaSuccess) return e;
+    }
+    return launch_pdl(attn_decode_mma_kernel<128, NST>, g, blk, smem, st, pdl, p);
   }
   if (DH == 256) {  // Gemma: 64 KB per K+V tile pair, three stages
-    const int smem = attn2_smem_bytes(256);
-    return cl ? launch_attn_decode2_t<256, 3, true>(p, n_ctas, smem, st, pdl)
-              : launch_attn_decode2_t<256, 3, false>(p, n_ctas, smem, st, pdl);
+    constexpr int NS3 = 3;
+    const int smem = 16 * 256 * 2 + NS3 * 2 * 64 * 256 * 2 + 1024 + 128;
+    {
+      cudaError_t e = set_smem(attn_decode_mma_kernel<256, NS3>, smem);
+      if (e != cudaSuccess) return e;
+    }
+    return launch_pdl(attn_decode_mma_kernel<256, NS3>, g, blk, smem, st, pdl, p);
   }
   if (DH == 64) {
-    const int smem = attn2_smem_bytes(64);
-    return cl ? launch_attn_decode2_t<64, 6, true>(p, n_ctas, smem, st, pdl)
-              : launch_attn_decode2_t<64, 6, false>(p, n_ctas, smem, st, pdl);
+    const int smem = 16 * 64 * 2 + NST * 2 * 64 * 64 * 2 + 1024 + 128;
+    {  // function attributes are per device: set on every launch (host-side, microseconds)
+      cudaError_t e = set_smem(attn_decode_mma_kernel<64, NST>, smem);
+      if (e != cudaSuccess) return e;
+    }
+    return launch_pdl(attn_decode_mma_kernel<64, NST>, g, blk, smem, st, pdl, p);
   }
   return cudaErrorInvalidValue;
 }
@@ -714,7 +689,6 @@ struct advspec_engine {
   int items_cap = 0, n_items = 0, n_slots = 0;
   // fused tensor-core decode attention: work decomposition of the current batch
   int a2_opg = 1, a2_n_og = 1, a2_n_splits = 1, a2_ctas = 0;
-  int a2_cluster = 0, a2_sfx = 1;  // cluster size (0: splits merged by the combine kernel), suffix items per group
   int h_slots[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int* s_pos = nullptr;     // [max_seqs] absolute position of each batch entry's next token
   CUtensorMap* kv_maps = nullptr;  // [L][2] device copies: prefix K / V tensor maps of each layer
@@ -1013,76 +987,12 @@ void build_items(advspec_engine* e, const std::vector<int>& slots, std::vector<A
 // shared by the whole group (one CTA per SM in total), each opponent's suffix is its own CTA.
 struct Attn2Plan {
   int opg, n_og, n_splits, ctas, n_slots;
-  int cluster;  // > 0: the items of a group form a thread-block cluster of this size (merge through DSMEM)
-  int sfx;      // suffix items per group in the grid
 };
-
-template <int DH, int NST>
-int max_clusters_of(int csize, int smem) {
-  auto kern = attn_decode_mma_kernel<DH, NST, true>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0;
-  if (csize > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(csize);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = csize;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  return n;
-}
-// How many clusters of `csize` CTAs of the decode attention kernel the device holds at once (cached per
-// device, head_dim and cluster size; 0 when that cluster size cannot be launched).
-int attn2_max_clusters(int device, int DH, int csize) {
-  static std::mutex mu;
-  static std::map<std::tuple<int, int, int>, int> cache;
-  std::lock_guard<std::mutex> lk(mu);
-  const auto key = std::make_tuple(device, DH, csize);
-  auto it = cache.find(key);
-  if (it != cache.end()) return it->second;
-  int n = 0;
-  const int smem = attn2_smem_bytes(DH);
-  if (DH == 256) n = max_clusters_of<256, 3>(csize, smem);
-  else if (DH == 64) n = max_clusters_of<64, 6>(csize, smem);
-  else n = max_clusters_of<128, 6>(csize, smem);
-  cache[key] = n;
-  return n;
-}
-
-int g_attn_cluster = 1;  // ADVSPEC_ATTN_IMPL=3 keeps the split + combine-kernel path everywhere (A/B)
-
-Attn2Plan plan_attn2_shape(int b, int n_heads, int n_kv_heads, int head_dim, int prefix_len, int device) {
+Attn2Plan plan_attn2_shape(int b, int n_heads, int n_kv_heads, int prefix_len, int device) {
   const int G = n_heads / n_kv_heads;
   const int opg = std::max(1, 16 / G);
   const int n_og = (b + opg - 1) / opg;
   const int groups = n_kv_heads * n_og;
-  const int DH = head_dim == 96 ? 128 : head_dim;
-  // Cluster path: a group's prefix splits and suffix items are one cluster of 16 or 8 CTAs, the whole grid
-  // resident at once.  (One KV head per tensor-parallel rank gives a single group — 16 CTAs cannot stream a
-  // 32K-token prefix; 32 MHA heads give more groups than clusters fit: both keep the combine kernel.)
-  const int sfx_c = std::min(opg, b);
-  if (g_attn_cluster) {
-    for (int C : {16, 8}) {
-      const int n_splits = C - sfx_c;
-      if (n_splits < 1 || n_splits > prefix_len || DH % C != 0) continue;
-      if (groups * C > num_sms(device)) continue;
-      if (groups * C < 48 && prefix_len >= 2048) continue;  // too few CTAs to stream a long prefix: split finer below
-      if (attn2_max_clusters(device, DH, C) < groups) continue;
-      return Attn2Plan{opg, n_og, n_splits, groups * C, n_splits + 1, C, sfx_c};
-    }
-  }
   // one wave of CTAs when that still cuts the prefix at least in two (GQA models); with many KV heads
   // (MHA: Phi-3 has 32) the prefix CTAs alone fill the wave and the short per-opponent suffix CTAs trail
   const int slots_left = std::max(groups, num_sms(device) - b * n_kv_heads);
@@ -1092,14 +1002,12 @@ Attn2Plan plan_attn2_shape(int b, int n_heads, int n_kv_heads, int head_dim, int
   if (n_splits < 2) n_splits = std::max(1, num_sms(device) / std::max(1, groups));
   n_splits = std::min(n_splits, std::max(1, prefix_len / g_attn_min_split));
   n_splits = std::min(n_splits, 300);
-  return Attn2Plan{opg, n_og, n_splits, groups * (n_splits + opg), n_splits + 1, 0, opg};
+  return Attn2Plan{opg, n_og, n_splits, groups * (n_splits + opg), n_splits + 1};
 }
 void plan_attn2(advspec_engine* e, const std::vector<int>& slots) {
   const auto& d = e->d;
   const int b = (int)slots.size();
-  const Attn2Plan pl = plan_attn2_shape(b, d.n_heads, d.n_kv_heads, d.head_dim, e->prefix_len, e->device);
-  e->a2_cluster = pl.cluster;
-  e->a2_sfx = pl.sfx;
+  const Attn2Plan pl = plan_attn2_shape(b, d.n_heads, d.n_kv_heads, e->prefix_len, e->device);
   e->a2_opg = pl.opg;
   e->a2_n_og = pl.n_og;
   e->a2_n_splits = pl.n_splits;
@@ -1187,9 +1095,6 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       a2.part_m = e->part_m;
       a2.part_l = e->part_l;
       a2.part_o = e->part_o;
-      a2.out = e->dattn;
-      a2.csize = e->a2_cluster;
-      a2.sfx_slots = e->a2_sfx;
       a2.b = b;
       a2.H = d.n_heads;
       a2.Hkv = d.n_kv_heads;
@@ -1202,15 +1107,11 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       a2.dh = d.head_dim;
       E_CUDA(e, launch_attn_decode2(a2, e->a2_ctas, d.head_dim, e->stream, true));
       ADV_TRACE(e->stream, "attn_decode_mma");
-      if (e->a2_cluster == 0) {
-        E_CUDA(e, launch_pdl(attn_decode_combine2_kernel, dim3(b * d.n_heads), dim3(128), 0, e->stream, true,
-                             (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o, e->dattn,
-                             e->n_slots, d.head_dim));
-        ADV_TRACE(e->stream, "attn_combine2");
-        e->launches -= 1;  // attention + combine instead of the rope + attention + combine counted below
-      } else {
-        e->launches -= 2;  // ONE kernel: RoPE + append + attention + merge of the splits inside the cluster
-      }
+      E_CUDA(e, launch_pdl(attn_decode_combine2_kernel, dim3(b * d.n_heads), dim3(128), 0, e->stream, true,
+                           (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o, e->dattn,
+                           e->n_slots, d.head_dim));
+      ADV_TRACE(e->stream, "attn_combine2");
+      e->launches -= 1;  // two kernels instead of rope + attention + combine (counted as 3 below)
     } else {
     E_CUDA(e, launch_pdl(rope_decode_kernel, dim3(b), dim3(256), 0, e->stream, true,
                            (const __nv_bfloat16*)e->dqkv, e->dq, suffix_k(e, l), suffix_v(e, l),
@@ -1250,7 +1151,7 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       chain_plan(&cp, b, &xs, &stg);
       E_CUDA(e, launch_chain(cp, b, xs, stg, e->device, e->stream, true));
       ADV_TRACE(e->stream, "gemv chain");
-      e->launches += 4;  // attention (+ combine) + chain
+      e->launches += 4;  // with the -1 above: attention + combine + chain = 3 launches per layer
       continue;
     }
     GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, tp_resadd_epi(e), d.act, d.norm_eps};
@@ -1455,7 +1356,6 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   g_gemv_impl = gi ? std::max(1, std::min(3, atoi(gi))) : 3;
   const char* ai = getenv("ADVSPEC_ATTN_IMPL");
   g_attn_impl = (ai && atoi(ai) == 1) ? 1 : 2;
-  g_attn_cluster = (ai && atoi(ai) == 3) ? 0 : 1;
   const char* xm = getenv("ADVSPEC_X_SMEM_MAX");
   g_x_smem_max = xm ? (size_t)atoll(xm) : 40000;
   g_gemm_narrow = getenv("ADVSPEC_GEMM_NARROW") != nullptr;
@@ -1993,7 +1893,7 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
     key.push_back(e->prefix_gen);
     { int tbits; memcpy(&tbits, &temperature, sizeof tbits); key.push_back(tbits); }
     key.push_back(eos_id);
-    const int64_t per_step = (e->attn_fused ? (e->a2_cluster ? 5 : 6) : 7) * (int64_t)d.n_layers + 3;
+    const int64_t per_step = (e->attn_fused ? 6 : 7) * (int64_t)d.n_layers + 3;
     if (e->use_graph) {
       if (!e->graph || e->graph_key != key) {
         if (e->graph) {
@@ -2393,11 +2293,7 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
       return ADVSPEC_ERR_INVALID;
     }
   if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
-  {
-    const char* ai = getenv("ADVSPEC_ATTN_IMPL");
-    g_attn_cluster = (ai && atoi(ai) == 3) ? 0 : 1;
-  }
-  const Attn2Plan pl = plan_attn2_shape(b, n_heads, n_kv_heads, head_dim, prefix_len, device);
+  const Attn2Plan pl = plan_attn2_shape(b, n_heads, n_kv_heads, prefix_len, device);
   CUtensorMap hm[2];
   const int64_t rows = (int64_t)n_kv_heads * prefix_stride;
   if (!make_tmap(&hm[0], prefix_k, rows, head_dim, head_dim, 64) ||
@@ -2444,9 +2340,6 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
   a2.part_m = pm;
   a2.part_l = plv;
   a2.part_o = po;
-  a2.out = reinterpret_cast<__nv_bfloat16*>(out);
-  a2.csize = pl.cluster;
-  a2.sfx_slots = pl.sfx;
   a2.b = b;
   a2.H = n_heads;
   a2.Hkv = n_kv_heads;
@@ -2458,7 +2351,7 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
   a2.scale = 1.0f / sqrtf((float)head_dim);
   a2.dh = head_dim;
   cudaError_t r = launch_attn_decode2(a2, pl.ctas, head_dim, 0, false);
-  if (r == cudaSuccess && pl.cluster == 0)
+  if (r == cudaSuccess)
     r = launch_pdl(attn_decode_combine2_kernel, dim3(b * n_heads), dim3(128), 0, (cudaStream_t)0, false,
                    (const float*)pm, (const float*)plv, (const float*)po, reinterpret_cast<__nv_bfloat16*>(out),
                    pl.n_slots, (int)head_dim);

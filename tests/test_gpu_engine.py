@@ -123,12 +123,12 @@ def test_batch_invariance_and_prefix_sharing(cuda_device, diag):
     for k, t in enumerate(cont):
         e.decode_step(ids, [t, (t + 1) % spec.vocab_size, t, (t + 7) % spec.vocab_size])
         lg = e.get_logits(4)
-        worst = max(worst, float(np.abs(lg[0] - solo[k]).max()), float(np.abs(lg[2] - solo[k]).max()))
+        worst = max(worst, rel_errors(lg[0], solo[k])[0], rel_errors(lg[2], solo[k])[0])
         if k > 0:
             break  # later steps have different histories for rows 1 and 3 only; rows 0, 2 stay comparable
-    diag["batch_invariance/maxabs"] = worst
+    diag["batch_invariance/max_over_std"] = worst
     e.close()
-    assert worst < 1e-3, worst
+    assert worst < 5e-3, worst  # of the logit std (the prefix is split the same way for b = 1 and b = 4)
 
 
 def test_decode_matches_prefill_of_same_tokens(cuda_device, diag):
@@ -193,8 +193,8 @@ def test_kernel_timeline_accounts_for_every_decode_kernel(cuda_device, diag):
     tl = measure.summarize(e.ktrace_read(), spec.n_layers)
     e.ktrace_enable(False)
     e.close()
-    # merge + L x (qkv, attention incl. its split merge, o, gate_up, down) + lm_head + vocabulary scan
-    assert tl["kernels_per_step"] == 5 * spec.n_layers + 3, tl
+    # merge + L x (qkv, attention, combine, o, gate_up, down) + lm_head + vocabulary scan
+    assert tl["kernels_per_step"] == 6 * spec.n_layers + 3, tl
     assert tl["gemv_launches_per_step"] == 4 * spec.n_layers + 1
     assert tl["steps"] >= 8 and tl["us_per_step"] > 0
 
@@ -285,11 +285,10 @@ def test_eos_stops_one_opponent_only(cuda_device):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [{"ADVSPEC_CHAIN": "1"}, {"ADVSPEC_L2_EVICT_FIRST": "0"}, {"ADVSPEC_NO_PDL": "1"},
-                                 {"ADVSPEC_ATTN_IMPL": "1"}, {"ADVSPEC_ATTN_IMPL": "3"}])
+                                 {"ADVSPEC_ATTN_IMPL": "1"}])
 def test_opt_in_decode_variants_give_the_default_logits(cuda_device, diag, monkeypatch, env):
     """The A/B knobs of DESIGN.md §4 (persistent GEMV chain, L2 policy, no programmatic launch, the
-    scalar decode attention, the split + combine-kernel attention instead of the cluster merge) change
-    scheduling, not arithmetic: teacher-forced decode logits must match
+    scalar decode attention) change scheduling, not arithmetic: teacher-forced decode logits must match
     the default path within the HF tolerance, and exactly where the kernels are the same."""
     rng = np.random.default_rng(21)
 
