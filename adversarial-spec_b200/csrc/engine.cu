@@ -42,9 +42,7 @@
 #include "common.cuh"
 #include "decode_kernels.cuh"
 #include "gemm_tcgen05.cuh"
-#include "gemv_chain.cuh"
 #include "gemv_mma.cuh"
-#include "gemv_stream.cuh"
 #include "tp_allreduce.cuh"
 
 using namespace advspec;
@@ -375,7 +373,7 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-int g_gemv_impl = 3;  // 3: bulk-async stream + tensor-core consumers (default); 2: same stream, CUDA-core consumers; 1: register loads (A/B only)
+int g_gemv_impl = 3;  // 3: bulk-async stream + tensor-core consumers (default); 1: register loads (fallback, A/B)
 
 cudaError_t launch_gemv_v1(const GemvParams& p, int b, int device, cudaStream_t st, bool pdl) {
   const int pairs = (p.N + 1) / 2;
@@ -392,34 +390,6 @@ cudaError_t launch_gemv_v1(const GemvParams& p, int b, int device, cudaStream_t 
     case 8: return launch_pdl(gemv_kernel<8, 1>, g, blk, 0, st, pdl, p);
   }
   return cudaErrorInvalidValue;
-}
-
-template <int B>
-cudaError_t launch_gemv_stream_t(const GemvParams& p, int device, cudaStream_t st, bool pdl) {
-  constexpr int kMaxDyn = 220 * 1024;  // leaves room for the kernel's static shared memory
-  {  // function attributes are per device: set on every launch (host-side, microseconds)
-    cudaError_t e = set_smem(gemv_stream_kernel<B>, kMaxDyn);
-    if (e != cudaSuccess) return e;
-  }
-  const size_t xbytes = (size_t)B * p.K * 2;
-  // the normalised activations (in_mode 1) always live in shared memory; plain bf16 inputs are
-  // copied there when they still leave a 3-stage ring, else read through L1 from global
-  int x_in_smem = 0;
-  size_t x_smem = 0;
-  if (p.in_mode == 1) {
-    x_smem = xbytes;
-  } else if (xbytes + 3 * (size_t)kGsStageBytes <= (size_t)kMaxDyn) {
-    x_in_smem = 1;
-    x_smem = xbytes;
-  }
-  x_smem = (x_smem + 127) / 128 * 128;
-  if (x_smem + 2 * (size_t)kGsStageBytes > (size_t)kMaxDyn) return cudaErrorInvalidValue;
-  int stages = (int)((kMaxDyn - x_smem) / kGsStageBytes);
-  stages = std::min(stages, kGsMaxStages);
-  const int pairs = (p.N + 1) / 2;
-  const int grid = std::max(1, std::min(num_sms(device), pairs));
-  const size_t dyn = (size_t)stages * kGsStageBytes + x_smem;
-  return launch_pdl(gemv_stream_kernel<B>, dim3(grid), dim3(kGsThreads), dyn, st, pdl, p, stages, x_in_smem);
 }
 
 int g_attn_min_split = 256;  // ADVSPEC_ATTN_MIN_SPLIT: fewest prefix tokens worth a split of their own
@@ -449,72 +419,6 @@ cudaError_t launch_gemv_mma_t(const GemvParams& p, int device, cudaStream_t st, 
   return launch_pdl(gemv_mma_kernel<B>, dim3(grid), dim3(kGmThreads), dyn, st, pdl, p, stages, x_in_smem);
 }
 
-int g_chain = 0;  // ADVSPEC_CHAIN=1: o-proj -> gate/up -> down -> next qkv (or lm_head) as phases of one launch
-
-// Fills the per-phase staging decisions; returns false when some phase cannot run in the chain kernel.
-bool chain_plan(ChainParams* cp, int b, size_t* x_smem_out, int* stages_out) {
-  constexpr int kMaxDyn = 232448 - 9 * 1024;
-  size_t x_smem = 0;
-  for (int i = 0; i < cp->n_ph; ++i) {
-    ChainPhase& q = cp->ph[i];
-    if (q.K % 16 != 0) return false;
-    const size_t xbytes = ((size_t)b * ((size_t)q.K * 2 + 16) + 127) / 128 * 128;
-    q.x_in_smem = 0;
-    if (q.in_mode == 1) {
-      x_smem = std::max(x_smem, xbytes);
-    } else if (xbytes + 2 * (size_t)kGmStageBytes <= (size_t)kMaxDyn && xbytes <= g_x_smem_max) {
-      q.x_in_smem = 1;
-      x_smem = std::max(x_smem, xbytes);
-    }
-  }
-  if (x_smem + 2 * (size_t)kGmStageBytes > (size_t)kMaxDyn) return false;
-  *x_smem_out = x_smem;
-  *stages_out = std::min<int>(kGmMaxStages, (int)((kMaxDyn - x_smem) / kGmStageBytes));
-  return true;
-}
-
-template <int B>
-cudaError_t launch_chain_t(const ChainParams& cp, size_t x_smem, int stages, int device, cudaStream_t st, bool pdl) {
-  constexpr int kMaxDyn = 232448 - 9 * 1024;
-  {  // function attributes are per device: set on every launch (host-side, microseconds)
-    cudaError_t e = set_smem(gemv_chain_kernel<B>, kMaxDyn);
-    if (e != cudaSuccess) return e;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(num_sms(device));  // one CTA per SM, all co-resident (the grid barrier needs it)
-  cfg.blockDim = dim3(kGmThreads);
-  cfg.dynamicSmemBytes = (size_t)stages * kGmStageBytes + x_smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[2];
-  int n = 0;
-  at[n].id = cudaLaunchAttributeCooperative;
-  at[n].val.cooperative = 1;
-  ++n;
-  if (pdl && g_use_pdl) {
-    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[n].val.programmaticStreamSerializationAllowed = 1;
-    ++n;
-  }
-  cfg.attrs = at;
-  cfg.numAttrs = n;
-  return cudaLaunchKernelEx(&cfg, gemv_chain_kernel<B>, cp, stages);
-}
-
-cudaError_t launch_chain(const ChainParams& cp, int b, size_t x_smem, int stages, int device, cudaStream_t st,
-                         bool pdl) {
-  switch (b) {
-    case 1: return launch_chain_t<1>(cp, x_smem, stages, device, st, pdl);
-    case 2: return launch_chain_t<2>(cp, x_smem, stages, device, st, pdl);
-    case 3: return launch_chain_t<3>(cp, x_smem, stages, device, st, pdl);
-    case 4: return launch_chain_t<4>(cp, x_smem, stages, device, st, pdl);
-    case 5: return launch_chain_t<5>(cp, x_smem, stages, device, st, pdl);
-    case 6: return launch_chain_t<6>(cp, x_smem, stages, device, st, pdl);
-    case 7: return launch_chain_t<7>(cp, x_smem, stages, device, st, pdl);
-    case 8: return launch_chain_t<8>(cp, x_smem, stages, device, st, pdl);
-  }
-  return cudaErrorInvalidValue;
-}
-
 cudaError_t launch_gemv_mma(const GemvParams& p, int b, int device, cudaStream_t st, bool pdl) {
   switch (b) {
     case 1: return launch_gemv_mma_t<1>(p, device, st, pdl);
@@ -530,27 +434,13 @@ cudaError_t launch_gemv_mma(const GemvParams& p, int b, int device, cudaStream_t
 }
 
 cudaError_t launch_gemv(const GemvParams& p, int b, int device, cudaStream_t st, bool pdl) {
-  if (g_gemv_impl == 3) {
-    const bool ok3 = (p.K % 16 == 0) &&
-                     (p.in_mode != 1 || ((size_t)b * ((size_t)p.K * 2 + 16) + 2 * (size_t)kGmStageBytes + 256 <= (size_t)(232448 - 9 * 1024)));
-    if (ok3) return launch_gemv_mma(p, b, device, st, pdl);
-    return launch_gemv_v1(p, b, device, st, pdl);
-  }
-  // fused-RMSNorm inputs live in shared memory next to the ring; shapes that cannot keep at least a
-  // 2-stage ring (no model in the table: K = d_model there) take the register-load kernel
-  const bool fits = p.in_mode != 1 || ((size_t)b * p.K * 2 + 2 * (size_t)kGsStageBytes + 256 <= (size_t)220 * 1024);
-  if (g_gemv_impl == 1 || !fits) return launch_gemv_v1(p, b, device, st, pdl);
-  switch (b) {
-    case 1: return launch_gemv_stream_t<1>(p, device, st, pdl);
-    case 2: return launch_gemv_stream_t<2>(p, device, st, pdl);
-    case 3: return launch_gemv_stream_t<3>(p, device, st, pdl);
-    case 4: return launch_gemv_stream_t<4>(p, device, st, pdl);
-    case 5: return launch_gemv_stream_t<5>(p, device, st, pdl);
-    case 6: return launch_gemv_stream_t<6>(p, device, st, pdl);
-    case 7: return launch_gemv_stream_t<7>(p, device, st, pdl);
-    case 8: return launch_gemv_stream_t<8>(p, device, st, pdl);
-  }
-  return cudaErrorInvalidValue;
+  // the bulk-async + tensor-core kernel serves every shape in the model table; the register-load kernel is the
+  // fallback for K % 16 != 0 or a fused-RMSNorm input too large to sit beside a 2-stage ring
+  // (ADVSPEC_GEMV_IMPL=1 forces it: the A/B the round-1 profiles refer to)
+  const bool ok3 = g_gemv_impl == 3 && (p.K % 16 == 0) &&
+                   (p.in_mode != 1 || ((size_t)b * ((size_t)p.K * 2 + 16) + 2 * (size_t)kGmStageBytes + 256 <= (size_t)(232448 - 9 * 1024)));
+  if (ok3) return launch_gemv_mma(p, b, device, st, pdl);
+  return launch_gemv_v1(p, b, device, st, pdl);
 }
 
 // -------------------------------------------------------------- attention
@@ -683,7 +573,6 @@ struct advspec_engine {
   float *dx = nullptr, *dx_save = nullptr, *dq = nullptr, *dlogits = nullptr;
   __nv_bfloat16 *dqkv = nullptr, *dattn = nullptr, *dh = nullptr;
   float *part_m = nullptr, *part_l = nullptr, *part_o = nullptr;
-  unsigned int* chain_bar = nullptr;  // grid-barrier words of gemv_chain_kernel
   unsigned int* gemm_sem = nullptr;   // ordering words of the prefill GEMM's K-split tail (zero between launches)
   AttnItem* items = nullptr;
   int items_cap = 0, n_items = 0, n_slots = 0;
@@ -921,7 +810,7 @@ void free_all(advspec_engine* e) {
   if (e->ar_gen) cudaFree(e->ar_gen);
   void* ptrs[] = {e->w, e->inv_freq, e->rope_cos, e->rope_sin, e->pkv, e->skv, e->p_tokens, e->p_x,
                   e->p_xn, e->p_qkv, e->p_attn, e->p_h, e->prefill_logits, e->dx, e->dx_save, e->dq,
-                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->chain_bar, e->gemm_sem, e->items, e->s_pos, e->kv_maps,
+                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->gemm_sem, e->items, e->s_pos, e->kv_maps,
                   e->s_slots, e->s_forced, e->s_seeds, e->s_suf_len, e->s_n_out, e->s_done,
                   e->s_cur_tok, e->s_out, e->samp_pack};
   for (void* p : ptrs)
@@ -1037,45 +926,10 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
     e->launches++;
     return r;
   };
-  // Chain mode: the four GEMVs between two attentions are phases of one persistent launch.
-  bool chain = g_chain && g_gemv_impl == 3 && !prof && e->attn_fused && e->tp_size == 1;
-  size_t chain_x_smem = 0;
-  int chain_stages = 0;
-  auto make_chain = [&](int l, ChainParams* cp) {
-    const LayerW w = layer_w(e, l);
-    const bool last = l + 1 == d.n_layers;
-    *cp = ChainParams{};
-    cp->ph[0] = ChainPhase{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, EPI_RESADD_F32, 0};
-    cp->ph[1] = ChainPhase{w.wgu, e->dx, w.mlp_norm, nullptr, e->dh, 2 * d.d_ff, dm, 1, EPI_GATED_BF16, 0};
-    cp->ph[2] = ChainPhase{w.wd, e->dh, nullptr, nullptr, e->dx, dm, d.d_ff, 0, EPI_RESADD_F32, 0};
-    if (last) {
-      cp->ph[3] = ChainPhase{lm_head_w(e), e->dx, final_norm_w(e), nullptr, e->dlogits, d.vocab_size, dm, 1, EPI_F32, 0};
-    } else {
-      const LayerW wn = layer_w(e, l + 1);
-      cp->ph[3] = ChainPhase{wn.wqkv, e->dx, wn.attn_norm, wn.bqkv, e->dqkv, QKV, dm, 1, EPI_BF16, 0};
-    }
-    cp->n_ph = 4;
-    cp->act = d.act;
-    cp->eps = d.norm_eps;
-    cp->bar = e->chain_bar;
-  };
-  if (chain) {
-    ChainParams cp;
-    make_chain(0, &cp);
-    chain = chain_plan(&cp, b, &chain_x_smem, &chain_stages);
-    if (chain && d.n_layers > 1) {
-      make_chain(d.n_layers - 1, &cp);
-      size_t xs2 = 0;
-      int st2 = 0;
-      chain = chain_plan(&cp, b, &xs2, &st2) && xs2 == chain_x_smem;
-    }
-  }
   for (int l = 0; l < d.n_layers; ++l) {
     const LayerW w = layer_w(e, l);
-    if (!chain || l == 0) {
     GemvParams g1{w.wqkv, e->dx, w.attn_norm, w.bqkv, e->dqkv, QKV, dm, 1, EPI_BF16, d.act, d.norm_eps};
     E_CUDA(e, gemv(g1));
-    }
     ADV_TRACE(e->stream, "gemv qkv");
     if (e->attn_fused) {
       AttnDecode2Params a2{};
@@ -1143,17 +997,6 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
                            e->dattn, e->n_slots, d.head_dim));
       ADV_TRACE(e->stream, "attn_combine");
     }
-    if (chain) {
-      ChainParams cp;
-      make_chain(l, &cp);
-      size_t xs = 0;
-      int stg = 0;
-      chain_plan(&cp, b, &xs, &stg);
-      E_CUDA(e, launch_chain(cp, b, xs, stg, e->device, e->stream, true));
-      ADV_TRACE(e->stream, "gemv chain");
-      e->launches += 4;  // with the -1 above: attention + combine + chain = 3 launches per layer
-      continue;
-    }
     GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, tp_resadd_epi(e), d.act, d.norm_eps};
     E_CUDA(e, gemv(g2));
     ADV_TRACE(e->stream, "gemv o");
@@ -1167,12 +1010,10 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
     ADV_TRACE(e->stream, "gemv down");
     e->launches += 3;
   }
-  if (!chain) {
-    GemvParams gl{lm_head_w(e), e->dx, final_norm_w(e), nullptr, e->dlogits, d.vocab_size, dm, 1, EPI_F32,
-                  d.act, d.norm_eps};
-    E_CUDA(e, gemv(gl));
-    ADV_TRACE(e->stream, "gemv lm_head");
-  }
+  GemvParams gl{lm_head_w(e), e->dx, final_norm_w(e), nullptr, e->dlogits, d.vocab_size, dm, 1, EPI_F32,
+                d.act, d.norm_eps};
+  E_CUDA(e, gemv(gl));
+  ADV_TRACE(e->stream, "gemv lm_head");
   if (prof) {
     E_CUDA(e, cudaStreamSynchronize(e->stream));
     float total = 0.f;
@@ -1353,7 +1194,7 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   g_trace = getenv("ADVSPEC_TRACE") != nullptr;
   // process-wide A/B knobs are re-read at every create (unset = default), so one process can compare them
   const char* gi = getenv("ADVSPEC_GEMV_IMPL");
-  g_gemv_impl = gi ? std::max(1, std::min(3, atoi(gi))) : 3;
+  g_gemv_impl = (gi && atoi(gi) == 1) ? 1 : 3;
   const char* ai = getenv("ADVSPEC_ATTN_IMPL");
   g_attn_impl = (ai && atoi(ai) == 1) ? 1 : 2;
   const char* xm = getenv("ADVSPEC_X_SMEM_MAX");
@@ -1367,8 +1208,6 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   g_attn_prefill_tc = tc ? atoi(tc) != 0 : true;
   const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT");
   g_attn_min_split = ms ? std::max(64, atoi(ms)) : 256;
-  const char* ch = getenv("ADVSPEC_CHAIN");
-  g_chain = ch ? atoi(ch) != 0 : 0;
 
   auto boot = [&]() -> advspec_status {
     const auto& d = e->d;
@@ -1426,8 +1265,6 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     E_CUDA(e, dmalloc(&e->items, (size_t)e->items_cap));
     E_CUDA(e, dmalloc(&e->gemm_sem, kGemmSemWords));
     E_CUDA(e, cudaMemsetAsync(e->gemm_sem, 0, kGemmSemWords * sizeof(unsigned int), e->stream));
-    E_CUDA(e, dmalloc(&e->chain_bar, 4));
-    E_CUDA(e, cudaMemsetAsync(e->chain_bar, 0, 4 * sizeof(unsigned int), e->stream));
     E_CUDA(e, dmalloc(&e->s_pos, B));
     E_CUDA(e, cudaMemsetAsync(e->s_pos, 0, B * sizeof(int), e->stream));
     e->attn_fused = g_attn_impl == 2 && (d.head_dim == 64 || d.head_dim == 96 || d.head_dim == 128 || d.head_dim == 256) && G <= 16 &&
@@ -2229,7 +2066,7 @@ advspec_status advspec_op_gemv(int32_t device, const void* W, const void* x, con
   }
   GemvParams p{reinterpret_cast<const __nv_bfloat16*>(W), x, reinterpret_cast<const float*>(norm_w),
                reinterpret_cast<const float*>(bias), y, N, K, in_mode, epilogue, act, eps};
-  if (const char* gi = getenv("ADVSPEC_GEMV_IMPL")) g_gemv_impl = std::max(1, std::min(3, atoi(gi)));
+  if (const char* gi = getenv("ADVSPEC_GEMV_IMPL")) g_gemv_impl = atoi(gi) == 1 ? 1 : 3;
   if (const char* ai = getenv("ADVSPEC_ATTN_IMPL")) g_attn_impl = atoi(ai) == 1 ? 1 : 2;
   if (const char* xm = getenv("ADVSPEC_X_SMEM_MAX")) g_x_smem_max = (size_t)atoll(xm);
   g_gemm_narrow = getenv("ADVSPEC_GEMM_NARROW") != nullptr;

@@ -42,3 +42,29 @@ def test_tensor_parallel_matches_hf_and_the_unsplit_engine(world):
         assert r["ranks_identical"], r
         # the all-reduce changes the summation order, so a near-tie may flip a token; most must agree
         assert r["greedy_token_agreement"] >= 0.75 and r["sampled_token_agreement"] >= 0.5, r
+
+
+@pytest.mark.gpu
+def test_tensor_parallel_cli_reads_one_stdin(tmp_path):
+    """`ADVSPEC_TP=2 torchrun ... debate.py critique < spec.md` — the ranks inherit ONE stdin, so
+    rank 0 reads the spec and broadcasts it; only rank 0 prints.  Same JSON as the unsplit CLI run."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from advspec_b200.tokenizer import SyntheticTokenizer, generate_spec
+
+    spec_text = generate_spec(SyntheticTokenizer(1024), 300, seed=5)
+    cli = str(ROOT / "adversarial-spec_b200" / "debate.py")
+    args = ["critique", "--models", "b200/tiny-gqa4,b200/tiny-gqa4", "--doc-type", "tech", "--json"]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", ADVSPEC_MAX_NEW_TOKENS="8", HOME=str(tmp_path))
+    solo = subprocess.run([sys.executable, cli, *args], input=spec_text, capture_output=True, text=True,
+                          env=dict(env, ADVSPEC_DEVICES="0"), cwd=tmp_path, timeout=600)
+    assert solo.returncode == 0, solo.stderr[-2000:]
+    tp = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                         "--master-addr", "127.0.0.1", "--master-port", str(29900 + os.getpid() % 90), cli, *args],
+                        input=spec_text, capture_output=True, text=True, env=dict(env, ADVSPEC_TP="2"), cwd=tmp_path,
+                        timeout=900)
+    assert tp.returncode == 0, (tp.stdout[-1500:], tp.stderr[-3000:])
+    a, b = json.loads(solo.stdout), json.loads(tp.stdout[tp.stdout.index("{"):])
+    assert [r["input_tokens"] for r in a["results"]] == [r["input_tokens"] for r in b["results"]]
+    assert all(r["output_tokens"] == 8 and r["error"] is None for r in b["results"])
+    assert tp.stdout.count('"all_agreed"') == 1, "only rank 0 reports"

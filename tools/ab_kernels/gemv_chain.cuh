@@ -13,7 +13,7 @@
 // may hold a copy from an earlier phase.
 #pragma once
 
-#include "gemv_mma.cuh"
+#include "../../adversarial-spec_b200/csrc/gemv_mma.cuh"
 
 namespace advspec {
 

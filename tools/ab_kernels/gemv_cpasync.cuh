@@ -11,9 +11,9 @@
 // (bias / residual add / gated activation / fp32 store) writes the rows.
 #pragma once
 
-#include "attn.cuh"  // cp_async16 / ldmatrix / mma wrappers
-#include "common.cuh"
-#include "decode_kernels.cuh"
+#include "../../adversarial-spec_b200/csrc/attn.cuh"  // cp_async16 / ldmatrix / mma wrappers
+#include "../../adversarial-spec_b200/csrc/common.cuh"
+#include "../../adversarial-spec_b200/csrc/decode_kernels.cuh"
 
 namespace advspec {
 

@@ -24,9 +24,9 @@
 // The first chunk's loads are issued before griddepcontrol.wait.
 #pragma once
 
-#include "attn.cuh"  // mma wrapper
-#include "common.cuh"
-#include "decode_kernels.cuh"
+#include "../../adversarial-spec_b200/csrc/attn.cuh"  // mma wrapper
+#include "../../adversarial-spec_b200/csrc/common.cuh"
+#include "../../adversarial-spec_b200/csrc/decode_kernels.cuh"
 
 namespace advspec {
 

@@ -12,8 +12,8 @@
 // multi-value butterfly.  Algorithmic bytes per launch: N*K*2, independent of b.
 #pragma once
 
-#include "common.cuh"
-#include "decode_kernels.cuh"
+#include "../../adversarial-spec_b200/csrc/common.cuh"
+#include "../../adversarial-spec_b200/csrc/decode_kernels.cuh"
 
 namespace advspec {
 

@@ -5,9 +5,9 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "../adversarial-spec_b200/csrc/gemv_mma.cuh"
-#include "../adversarial-spec_b200/csrc/gemv_stream.cuh"
-#include "../adversarial-spec_b200/csrc/gemv_cpasync.cuh"
-#include "../adversarial-spec_b200/csrc/gemv_rmma.cuh"
+#include "ab_kernels/gemv_stream.cuh"
+#include "ab_kernels/gemv_cpasync.cuh"
+#include "ab_kernels/gemv_rmma.cuh"
 using namespace advspec;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
