@@ -13,7 +13,10 @@
 //               MN-major operand; O accumulates in TMEM across all tiles
 // Warp roles: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-9 softmax/epilogue.
 // S is double-buffered in TMEM so QK^T of tile j+1 runs under the softmax of tile j.
-// TMEM columns: S0 [0,128) S1 [128,256) O [256,384).  head_dim 128 only (64/96/256 use attn.cuh).
+// TMEM columns: S0 [0,128) S1 [128,256) O [256,384).  head_dim 128, and 64 / 96 in the same 128-wide tiles:
+// Q K^T issues only head_dim/16 k-steps (whatever the TMA box holds past the head is never multiplied), the K/V
+// tensor maps are head_dim wide so the box columns past it arrive as zeros, and O's columns past head_dim are
+// not written (Phi-3's 32 x 96 heads).  head_dim 256 (Gemma) uses attn.cuh.
 // Shared memory: Q, P x2, (K, V) x2 stages = 7 x 32 KB + barriers + the row-maximum exchange = the whole
 // 227 KB of the SM.
 #pragma once
@@ -76,10 +79,11 @@ struct AttnPrefillTcParams {
   int n_q, q_pos0, H, Hkv;
   int kv_rows_per_head;  // kv_stride: row of (kv head hk, token t) in the K/V tensor maps = hk*kv_rows_per_head + t
   float scale;
+  int dh;  // head_dim: 64, 96 or 128
 };
 
-// tmQ: [n_q rows][ldq cols] bf16 (head h at column h*128), box 64 cols x 128 rows, 128B swizzle.
-// tmK/tmV: [Hkv*kv_stride rows][128 cols], box 64 cols x 128 rows, 128B swizzle.
+// tmQ: [n_q rows][ldq cols] bf16 (head h at column h*dh), box 64 cols x 128 rows, 128B swizzle.
+// tmK/tmV: [Hkv*kv_stride rows][dh cols], box 64 cols x 128 rows, 128B swizzle.
 __global__ void __launch_bounds__(kAtThreads, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, AttnPrefillTcParams p) {
@@ -145,8 +149,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp == 0 && lane == 0) {
     // ------------------------------ TMA producer ------------------------------
     mbar_arrive_expect_tx(q_full, kAtTile);
-    tma_load_2d(sQ, &tmQ, q_full, h * kAtDH, q0);
-    tma_load_2d(sQ + kAtHalf, &tmQ, q_full, h * kAtDH + 64, q0);
+    tma_load_2d(sQ, &tmQ, q_full, h * p.dh, q0);
+    tma_load_2d(sQ + kAtHalf, &tmQ, q_full, h * p.dh + 64, q0);
     for (int t = 0; t < n_t; ++t) {
       const int s = t % kAtStages;
       mbar_wait(&kv_empty[s], (((uint32_t)(t / kAtStages)) & 1u) ^ 1u, 0x900u + s);
@@ -166,8 +170,10 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait(&kv_full[s], ((uint32_t)(t / kAtStages)) & 1u, 0xA00u + s);
       mbar_wait(&s_empty[b], (((uint32_t)(t >> 1)) & 1u) ^ 1u, 0xA10u + b);
       tc_fence_after();
+      const int n_ks = p.dh / 16;  // k-steps of the head dimension actually present
 #pragma unroll
       for (int k = 0; k < kAtDH / 16; ++k) {
+        if (k >= n_ks) break;
         const uint32_t off = (uint32_t)(k >> 2) * kAtHalf + (uint32_t)(k & 3) * 32u;  // 64-dim half, 32 B per k-step
         tc_mma_f16(tS[b], make_smem_desc_sw128(smem_u32(sQ) + off), make_smem_desc_sw128(smem_u32(sK + s * kAtTile) + off),
                    idesc_qk, k != 0 ? 1u : 0u);
@@ -285,14 +291,14 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tc_fence_after();
     const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
     const int qr = q0 + row;
-    __nv_bfloat16* dst = p.out + (int64_t)qr * (p.H * kAtDH) + h * kAtDH + ch * 64;
+    __nv_bfloat16* dst = p.out + (int64_t)qr * (p.H * p.dh) + h * p.dh + ch * 64;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       uint32_t ov[32];
       __syncwarp();
       tmem_ld_32x32(tO + lane_off + col_off + (uint32_t)(c * 32), ov);
       tmem_ld_wait();
-      if (qr < p.n_q) {
+      if (qr < p.n_q && ch * 64 + c * 32 < p.dh) {
 #pragma unroll
         for (int e = 0; e < 32; e += 8) {
           uint4 o;

@@ -470,13 +470,15 @@ cudaError_t launch_attn_prefill(const AttnPrefillParams& p, int DH, int impl, cu
   return cudaGetLastError();
 }
 
-// Prompt attention on tcgen05 (head_dim 128): Q from [n_q][ldq] rows, K/V from [Hkv*kv_stride][128] rows.
+// Prompt attention on tcgen05 (head_dim 64 / 96 / 128): Q from [n_q][ldq] rows, K/V from [Hkv*kv_stride][dh] rows.
 cudaError_t launch_attn_prefill_tc(const void* q, int64_t ldq, const void* kc, const void* vc, int64_t kv_stride,
-                                   void* out, int n_q, int q_pos0, int H, int Hkv, cudaStream_t st, std::string* err) {
+                                   void* out, int n_q, int q_pos0, int H, int Hkv, int dh, cudaStream_t st,
+                                   std::string* err) {
   CUtensorMap tq, tk, tv;
   const int64_t kv_rows = (int64_t)Hkv * kv_stride;
-  if (!make_tmap(&tq, q, n_q, (int64_t)H * 128, ldq, 128) || !make_tmap(&tk, kc, kv_rows, 128, 128, 128) ||
-      !make_tmap(&tv, vc, kv_rows, 128, 128, 128)) {
+  // the Q map spans the whole row (ldq columns): the second 64-column box of the last head may reach into K's columns
+  if (!make_tmap(&tq, q, n_q, ldq, ldq, 128) || !make_tmap(&tk, kc, kv_rows, dh, dh, 128) ||
+      !make_tmap(&tv, vc, kv_rows, dh, dh, 128)) {
     if (err) *err = "cuTensorMapEncodeTiled failed (attention)";
     return cudaErrorInvalidValue;
   }
@@ -485,7 +487,7 @@ cudaError_t launch_attn_prefill_tc(const void* q, int64_t ldq, const void* kc, c
     if (e != cudaSuccess) return e;
   }
   AttnPrefillTcParams p{reinterpret_cast<__nv_bfloat16*>(out), n_q, q_pos0, H, Hkv, (int)kv_stride,
-                        1.0f / sqrtf(128.0f)};
+                        1.0f / sqrtf((float)dh), dh};
   dim3 grid((n_q + kAtBM - 1) / kAtBM, H);
   attn_prefill_tc_kernel<<<grid, kAtThreads, kAtSmem, st>>>(tq, tk, tv, p);
   return cudaGetLastError();
@@ -772,10 +774,10 @@ advspec_status prefill_chunk(advspec_engine* e, int m, int pos0) {
     E_CUDA(e, cudaGetLastError());
     AttnPrefillParams ap{e->p_qkv, QKV, prefix_k(e, l), prefix_v(e, l), d.max_prefix_tokens, e->p_attn,
                          m, pos0, d.n_heads, d.n_kv_heads, 1.0f / sqrtf((float)d.head_dim), d.head_dim};
-    if (d.head_dim == 128 && g_attn_prefill_tc && !(e->debug_flags & 2)) {
+    if (d.head_dim <= 128 && g_attn_prefill_tc && !(e->debug_flags & 2)) {
       std::string why;
       cudaError_t r = launch_attn_prefill_tc(e->p_qkv, QKV, prefix_k(e, l), prefix_v(e, l), d.max_prefix_tokens,
-                                             e->p_attn, m, pos0, d.n_heads, d.n_kv_heads, e->stream, &why);
+                                             e->p_attn, m, pos0, d.n_heads, d.n_kv_heads, d.head_dim, e->stream, &why);
       if (r != cudaSuccess) {
         e->fail("tcgen05 attention launch failed: %s %s", cudaGetErrorString(r), why.c_str());
         return ADVSPEC_ERR_CUDA;
@@ -2093,12 +2095,13 @@ advspec_status advspec_op_attn_prefill(int32_t device, const void* q, int64_t ld
                       1.0f / sqrtf((float)head_dim), head_dim};
   cudaError_t r;
   if (impl == 2) {
-    if (head_dim != 128) {
-      g_create_error = "op_attn_prefill: the tcgen05 kernel serves head_dim 128 only";
+    if (head_dim != 128 && head_dim != 96 && head_dim != 64) {
+      g_create_error = "op_attn_prefill: the tcgen05 kernel serves head_dim 64, 96 and 128";
       return ADVSPEC_ERR_INVALID;
     }
     std::string why;
-    r = launch_attn_prefill_tc(q, ldq, kcache, vcache, kv_stride, out, n_q, q_pos0, n_heads, n_kv_heads, 0, &why);
+    r = launch_attn_prefill_tc(q, ldq, kcache, vcache, kv_stride, out, n_q, q_pos0, n_heads, n_kv_heads, head_dim, 0,
+                               &why);
   } else {
     r = launch_attn_prefill(p, head_dim, impl, 0, nullptr);
   }

@@ -272,7 +272,7 @@ advspec_status advspec_op_gemv(int32_t device, const void *W, const void *x,
  * h*head_dim), K/V cache: bf16 [n_kv_heads][kv_stride][head_dim]; query i sits
  * at position q_pos0+i and sees keys 0..q_pos0+i.  out: bf16 [n_q][n_heads*
  * head_dim].  impl 0 = mma.sync kernel, 1 = scalar check kernel, 2 = tcgen05 kernel
- * (head_dim 128 only). */
+ * (head_dim 64, 96 or 128). */
 advspec_status advspec_op_attn_prefill(int32_t device, const void *q,
                                        int64_t ldq, const void *kcache,
                                        const void *vcache, int64_t kv_stride,
