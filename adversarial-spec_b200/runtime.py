@@ -60,44 +60,54 @@ def tp_world() -> tuple[int, int]:
     return _env_int("RANK", 0), tp
 
 
-def broadcast_object(obj, src: int = 0):
-    """Plumbing for the tensor-parallel CLI: one Python object from rank `src` to every rank of the
-    torchrun job (gloo; the group is created here if the engine has not created it yet)."""
+_plumbing = {"group": None}
+
+
+def plumbing_group():
+    """A gloo process group for the few bytes of host-side plumbing (NCCL id, CUDA IPC handles, the spec text):
+    the default group when it already is gloo, else a gloo group created beside it (every rank must call this
+    at the same point — the callers below are collective anyway).  Host tensors only, so it does not matter
+    which thread or CUDA device the caller is on."""
     import torch.distributed as dist
 
     if not dist.is_initialized():
         dist.init_process_group("gloo")
+    if _plumbing["group"] is None:
+        _plumbing["group"] = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
+    return _plumbing["group"]
+
+
+def broadcast_object(obj, src: int = 0):
+    """Plumbing for the tensor-parallel CLI: one Python object from rank `src` to every rank of the
+    torchrun job."""
+    import torch.distributed as dist
+
     box = [obj]
-    dist.broadcast_object_list(box, src=src)
+    dist.broadcast_object_list(box, src=src, group=plumbing_group())
     return box[0]
 
 
 def create_tp_engine(spec: ModelSpec, device: int, max_prefix_tokens: int, max_new_tokens: int, max_seqs: int,
                      tp_rank: int, tp_size: int) -> eng.Engine:
     """This rank's handle of a tensor-parallel engine: rank 0 draws the NCCL id, torch.distributed
-    (the plumbing; any backend) carries it to the others, every rank joins (include/advspec_engine.h)."""
+    (the plumbing; gloo, host tensors) carries it to the others, every rank joins (include/advspec_engine.h)."""
     import torch
     import torch.distributed as dist
 
-    if not dist.is_initialized():
-        dist.init_process_group("gloo")  # 128 bytes of plumbing; the engine owns its NCCL communicator
+    pg = plumbing_group()
     e = eng.Engine(spec, device, max_prefix_tokens, max_new_tokens, max_seqs, tp_rank=tp_rank, tp_size=tp_size)
     buf = torch.zeros(128, dtype=torch.uint8)
     if tp_rank == 0:
         buf = torch.frombuffer(bytearray(eng.Engine.tp_unique_id()), dtype=torch.uint8).clone()
-    if dist.get_backend() == "nccl":
-        buf = buf.cuda(device)
-    dist.broadcast(buf, src=0)
-    e.tp_init(bytes(buf.cpu().numpy().tobytes()))
+    dist.broadcast(buf, src=0, group=pg)
+    e.tp_init(bytes(buf.numpy().tobytes()))
     if os.environ.get("ADVSPEC_TP_NCCL_ONLY") is None:
         # decode-step exchange over NVLink peer memory: gather every rank's CUDA IPC handle
         mine = torch.frombuffer(bytearray(e.tp_ipc_export()), dtype=torch.uint8).clone()
-        if dist.get_backend() == "nccl":
-            mine = mine.cuda(device)
         allh = [torch.zeros_like(mine) for _ in range(tp_size)]
-        dist.all_gather(allh, mine)
-        e.tp_ipc_import([bytes(h.cpu().numpy().tobytes()) for h in allh])
-        dist.barrier()  # nobody pushes before everybody has mapped
+        dist.all_gather(allh, mine, group=pg)
+        e.tp_ipc_import([bytes(h.numpy().tobytes()) for h in allh])
+        dist.barrier(group=pg)  # nobody pushes before everybody has mapped
     return e
 
 
