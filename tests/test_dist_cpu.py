@@ -164,3 +164,45 @@ def test_tensor_parallel_sharding_matches_whole_model_world2():
     for p in ps:
         p.join(30)
     assert err < 1e-4 * max(std, 1.0), (err, std)
+
+
+def _tp_cli_worker(rank, world, port, q, stdin_path):
+    """One rank of `ADVSPEC_TP=2 torchrun debate.py critique`: only rank 0 is given the spec on stdin."""
+    import io
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import advspec_loader
+
+    advspec_loader.load()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), ADVSPEC_TP=str(world))
+    from advspec_b200 import debate, runtime
+
+    sys.stdin = open(stdin_path) if rank == 0 else io.StringIO("")  # torchrun children share ONE stdin
+    spec = debate.read_spec_from_stdin()
+    # the same gloo group then carries the engine's NCCL id / IPC handles (runtime.create_tp_engine)
+    import torch
+    import torch.distributed as dist
+
+    buf = torch.full((4,), float(rank))
+    dist.broadcast(buf, src=0, group=runtime.plumbing_group())
+    dist.barrier(group=runtime.plumbing_group())
+    dist.destroy_process_group()
+    q.put((rank, spec, buf.tolist()))
+
+
+def test_tensor_parallel_cli_broadcasts_the_one_stdin(tmp_path):
+    """under torchrun the ranks inherit one stdin; rank 0 reads the spec and every rank gets it."""
+    text = "  # Spec\n\nThe service must store data.\n"
+    p = tmp_path / "spec.md"
+    p.write_text(text)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tp_cli_worker, args=(r, 2, 29647, q, str(p))) for r in range(2)]
+    [pr.start() for pr in procs]
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    [pr.join(timeout=60) for pr in procs]
+    assert [g[1] for g in got] == [text.strip()] * 2
+    assert got[1][2] == [0.0] * 4
