@@ -30,10 +30,10 @@ constexpr int kAtBM = 128, kAtBN = 128, kAtDH = 128;
 constexpr int kAtStages = 2;
 constexpr int kAtHalf = 128 * 64 * 2;               // bytes of a [128 rows][64 elems] half tile (16 KB)
 constexpr int kAtTile = 2 * kAtHalf;                // 32 KB: Q, K, V or P tile
-constexpr int kAtBarBytes = 128;
+constexpr int kAtBarBytes = 256;
 constexpr int kAtMxBytes = 2 * 2 * 128 * 4;         // [tile parity][column half][row] row-maximum exchange
-// Q, P x2, K/V stages, barriers, exchange, alignment slack (the base is 128-byte aligned: at most 896 bytes)
-constexpr int kAtSmem = kAtTile * (3 + 2 * kAtStages) + kAtBarBytes + kAtMxBytes + 896;
+// Q, P x2, K/V stages, barriers, exchange, alignment slack (the base is 256-byte aligned: at most 768 bytes)
+constexpr int kAtSmem = kAtTile * (3 + 2 * kAtStages) + kAtBarBytes + kAtMxBytes + 768;
 static_assert(kAtSmem <= 232448, "the prompt-attention CTA needs the whole 227 KB");
 constexpr int kAtThreads = 320;  // TMA warp, MMA warp, 8 softmax warps (2 threads per query row)
 
@@ -74,6 +74,8 @@ __device__ __forceinline__ float exp2_poly3(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+__device__ int g_attn_poly = 1;  // ADVSPEC_ATTN_POLY=0: all exponentials on the MUFU (A/B)
+
 struct AttnPrefillTcParams {
   __nv_bfloat16* out;  // [n_q][H*128]
   int n_q, q_pos0, H, Hkv;
@@ -87,7 +89,7 @@ struct AttnPrefillTcParams {
 __global__ void __launch_bounds__(kAtThreads, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, AttnPrefillTcParams p) {
-  extern __shared__ __align__(128) uint8_t at_raw[];
+  extern __shared__ __align__(256) uint8_t at_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
   uint8_t* sP = smem + kAtTile;                         // [2]: tile parity
@@ -95,9 +97,13 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint8_t* sV = smem + (3 + kAtStages) * kAtTile;       // [stages]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (3 + 2 * kAtStages) * kAtTile);
   uint64_t* q_full = bars;                 // 1
-  uint64_t* kv_full = bars + 1;            // [stages]
-  uint64_t* kv_empty = bars + 1 + kAtStages;  // [stages]
-  uint64_t* s_full = bars + 1 + 2 * kAtStages;   // [2]
+  // K and V of a stage have their own barriers: the K slot is free as soon as Q K^T of its tile has retired
+  // (long before P V), so the load of K(j+2) — and with it S(j+2) — no longer waits behind softmax and P V of tile j
+  uint64_t* k_full = bars + 1;             // [stages]
+  uint64_t* v_full = k_full + kAtStages;   // [stages]
+  uint64_t* k_empty = v_full + kAtStages;  // [stages]
+  uint64_t* v_empty = k_empty + kAtStages; // [stages]
+  uint64_t* s_full = v_empty + kAtStages;  // [2]
   uint64_t* s_empty = s_full + 2;          // [2]
   uint64_t* p_full = s_empty + 2;          // [2]: P of tile j is in buffer j & 1
   uint64_t* pv_done = p_full + 2;          // [2]: P V of tile j retired (frees P buffer j & 1 and, in order, O)
@@ -122,8 +128,10 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < kAtStages; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&k_full[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
@@ -146,20 +154,24 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t tS[2] = {tmem_base, tmem_base + 128u};
   const uint32_t tO = tmem_base + 256u;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    mbar_arrive_expect_tx(q_full, kAtTile);
-    tma_load_2d(sQ, &tmQ, q_full, h * p.dh, q0);
-    tma_load_2d(sQ + kAtHalf, &tmQ, q_full, h * p.dh + 64, q0);
+  if (warp == 0 && (lane == 0 || lane == 16)) {
+    // ------------------------------ TMA producers: lane 0 streams K (and Q), lane 16 streams V -----------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kAtTile);
+      tma_load_2d(sQ, &tmQ, q_full, h * p.dh, q0);
+      tma_load_2d(sQ + kAtHalf, &tmQ, q_full, h * p.dh + 64, q0);
+    }
+    uint8_t* dst = lane == 0 ? sK : sV;
+    const CUtensorMap* tm = lane == 0 ? &tmK : &tmV;
+    uint64_t* full = lane == 0 ? k_full : v_full;
+    uint64_t* empty = lane == 0 ? k_empty : v_empty;
     for (int t = 0; t < n_t; ++t) {
       const int s = t % kAtStages;
-      mbar_wait(&kv_empty[s], (((uint32_t)(t / kAtStages)) & 1u) ^ 1u, 0x900u + s);
-      mbar_arrive_expect_tx(&kv_full[s], 2 * kAtTile);
+      mbar_wait(&empty[s], (((uint32_t)(t / kAtStages)) & 1u) ^ 1u, 0x900u + s + (lane ? 8 : 0));
+      mbar_arrive_expect_tx(&full[s], kAtTile);
       const int row = hk * p.kv_rows_per_head + t * kAtBN;
-      tma_load_2d(sK + s * kAtTile, &tmK, &kv_full[s], 0, row);
-      tma_load_2d(sK + s * kAtTile + kAtHalf, &tmK, &kv_full[s], 64, row);
-      tma_load_2d(sV + s * kAtTile, &tmV, &kv_full[s], 0, row);
-      tma_load_2d(sV + s * kAtTile + kAtHalf, &tmV, &kv_full[s], 64, row);
+      tma_load_2d(dst + s * kAtTile, tm, &full[s], 0, row);
+      tma_load_2d(dst + s * kAtTile + kAtHalf, tm, &full[s], 64, row);
     }
   } else if (warp == 1 && lane == 0) {
     // ------------------------------ MMA issuer --------------------------------
@@ -167,7 +179,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128) | (1u << 16);  // B (= V) is MN-major
     auto issue_qk = [&](int t) {
       const int s = t % kAtStages, b = t & 1;
-      mbar_wait(&kv_full[s], ((uint32_t)(t / kAtStages)) & 1u, 0xA00u + s);
+      mbar_wait(&k_full[s], ((uint32_t)(t / kAtStages)) & 1u, 0xA00u + s);
       mbar_wait(&s_empty[b], (((uint32_t)(t >> 1)) & 1u) ^ 1u, 0xA10u + b);
       tc_fence_after();
       const int n_ks = p.dh / 16;  // k-steps of the head dimension actually present
@@ -179,6 +191,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                    idesc_qk, k != 0 ? 1u : 0u);
       }
       tc_commit(&s_full[b]);
+      tc_commit(&k_empty[s]);  // the K slot is reusable once these MMAs retire
     };
     mbar_wait(q_full, 0, 0xA20u);
     issue_qk(0);
@@ -186,6 +199,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (j + 1 < n_t) issue_qk(j + 1);
       const int s = j % kAtStages, pb = j & 1;
       mbar_wait(&p_full[pb], ((uint32_t)(j >> 1)) & 1u, 0xA30u + pb);
+      mbar_wait(&v_full[s], ((uint32_t)(j / kAtStages)) & 1u, 0xA40u + s);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < kAtBN / 16; ++k) {
@@ -195,7 +209,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                    make_smem_desc_sw128_mn(smem_u32(sV + s * kAtTile) + offv, kAtHalf), idesc_pv, (j | k) != 0 ? 1u : 0u);
       }
       tc_commit(&pv_done[pb]);
-      tc_commit(&kv_empty[s]);
+      tc_commit(&v_empty[s]);
     }
   } else if (warp >= 2) {
     // ------------------------------ softmax + epilogue ------------------------
@@ -206,6 +220,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t col_off = (uint32_t)(ch * 64);
     const int qpos = p.q_pos0 + q0 + row;
     const float sl2 = p.scale * 1.4426950408889634f;
+    const bool poly = g_attn_poly != 0;
     float m_used = -INFINITY;  // row maximum the exponentials are currently taken against (raw score units)
     float l_run = 0.f;         // this thread's share of the row sum
     for (int j = 0; j < n_t; ++j) {
@@ -267,7 +282,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float x = __uint_as_float(sv[c8 * 8 + e]) * sl2 - m_off;
-          pv[e] = (c8 & 1) ? exp2_poly3(x) : exp2f(x);
+          pv[e] = ((c8 & 1) && poly) ? exp2_poly3(x) : exp2f(x);
           rs += pv[e];
         }
         uint4 o;

@@ -1,0 +1,258 @@
+// attn_prefill_tc_v1.cuh (round-1 pipeline: single-buffered P, one K/V barrier pair per stage; A/B) — causal flash attention for the prompt on the 5th-gen tensor cores.
+//
+// One CTA = 128 query rows of one head; keys in tiles of 128.  Per tile
+//   S = Q K^T   tcgen05.mma 128x128x128, Q and K K-major from TMA-swizzled shared memory, S in TMEM
+//   softmax     8 warps, TWO THREADS PER QUERY ROW (64 keys each; the exponentials are MUFU-bound, so the
+//               row is split): tcgen05.ld the scores, mask, exp2 against a
+//               lazily-updated row maximum (rescale O only when the maximum grew by > 2^8), write P
+//               (bf16) back to shared memory in the 128B-swizzled K-major layout
+//   O += P V    tcgen05.mma 128x128x128, A = P (K-major), B = V straight from its [key][dim] tile as an
+//               MN-major operand; O accumulates in TMEM across all tiles
+// Warp roles: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-9 softmax/epilogue.
+// S is double-buffered in TMEM so QK^T of tile j+1 runs under the softmax of tile j.
+// TMEM columns: S0 [0,128) S1 [128,256) O [256,384).  head_dim 128 only (64/96/256 use attn.cuh).
+#pragma once
+
+#include "attn_prefill_tc.cuh"  // helpers + AttnPrefillTcParams
+
+namespace advspec {
+
+constexpr int kA1BM = 128, kA1BN = 128, kA1DH = 128;
+constexpr int kA1Stages = 2;
+constexpr int kA1Half = 128 * 64 * 2;               // bytes of a [128 rows][64 elems] half tile (16 KB)
+constexpr int kA1Tile = 2 * kA1Half;                // 32 KB: Q, K, V or P tile
+constexpr int kA1Smem = kA1Tile * (2 + 2 * kA1Stages) + 256 + 1024;  // Q, P, K/V stages, barriers, alignment
+constexpr int kA1Threads = 320;  // TMA warp, MMA warp, 8 softmax warps (2 threads per query row)
+
+// tmQ: [n_q rows][ldq cols] bf16 (head h at column h*128), box 64 cols x 128 rows, 128B swizzle.
+// tmK/tmV: [Hkv*kv_stride rows][128 cols], box 64 cols x 128 rows, 128B swizzle.
+__global__ void __launch_bounds__(kA1Threads, 1)
+attn_prefill_tc_v1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, AttnPrefillTcParams p) {
+  extern __shared__ uint8_t at_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sP = smem + kA1Tile;
+  uint8_t* sK = smem + 2 * kA1Tile;                     // [stages]
+  uint8_t* sV = smem + (2 + kA1Stages) * kA1Tile;       // [stages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + 2 * kA1Stages) * kA1Tile);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* kv_full = bars + 1;            // [stages]
+  uint64_t* kv_empty = bars + 1 + kA1Stages;  // [stages]
+  uint64_t* s_full = bars + 1 + 2 * kA1Stages;   // [2]
+  uint64_t* s_empty = s_full + 2;          // [2]
+  uint64_t* p_full = s_empty + 2;          // 1
+  uint64_t* pv_done = p_full + 1;          // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  __shared__ float s_mx[2][2][128];  // [tile parity][column half][row]: row-maximum exchange between the two threads of a row
+  __shared__ float s_lsum[2][128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_qtiles = (p.n_q + kA1BM - 1) / kA1BM;
+  const int qt = n_qtiles - 1 - (int)blockIdx.x;  // heaviest (latest) tiles first
+  const int q0 = qt * kA1BM;
+  const int h = blockIdx.y;
+  const int hk = h / (p.H / p.Hkv);
+  const int total_kv = p.q_pos0 + p.n_q;
+  const int kv_needed = min(p.q_pos0 + q0 + kA1BM, total_kv);  // keys any row of this tile may see
+  const int n_t = (kv_needed + kA1BN - 1) / kA1BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kA1Stages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 256);
+    }
+    mbar_init(p_full, 256);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS[2] = {tmem_base, tmem_base + 128u};
+  const uint32_t tO = tmem_base + 256u;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    mbar_arrive_expect_tx(q_full, kA1Tile);
+    tma_load_2d(sQ, &tmQ, q_full, h * p.dh, q0);
+    tma_load_2d(sQ + kA1Half, &tmQ, q_full, h * p.dh + 64, q0);
+    for (int t = 0; t < n_t; ++t) {
+      const int s = t % kA1Stages;
+      mbar_wait(&kv_empty[s], (((uint32_t)(t / kA1Stages)) & 1u) ^ 1u, 0x900u + s);
+      mbar_arrive_expect_tx(&kv_full[s], 2 * kA1Tile);
+      const int row = hk * p.kv_rows_per_head + t * kA1BN;
+      tma_load_2d(sK + s * kA1Tile, &tmK, &kv_full[s], 0, row);
+      tma_load_2d(sK + s * kA1Tile + kA1Half, &tmK, &kv_full[s], 64, row);
+      tma_load_2d(sV + s * kA1Tile, &tmV, &kv_full[s], 0, row);
+      tma_load_2d(sV + s * kA1Tile + kA1Half, &tmV, &kv_full[s], 64, row);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------ MMA issuer --------------------------------
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128) | (1u << 16);  // B (= V) is MN-major
+    auto issue_qk = [&](int t) {
+      const int s = t % kA1Stages, b = t & 1;
+      mbar_wait(&kv_full[s], ((uint32_t)(t / kA1Stages)) & 1u, 0xA00u + s);
+      mbar_wait(&s_empty[b], (((uint32_t)(t >> 1)) & 1u) ^ 1u, 0xA10u + b);
+      tc_fence_after();
+      const int n_ks = p.dh / 16;
+#pragma unroll
+      for (int k = 0; k < kA1DH / 16; ++k) {
+        if (k >= n_ks) break;
+        const uint32_t off = (uint32_t)(k >> 2) * kA1Half + (uint32_t)(k & 3) * 32u;  // 64-dim half, 32 B per k-step
+        tc_mma_f16(tS[b], make_smem_desc_sw128(smem_u32(sQ) + off), make_smem_desc_sw128(smem_u32(sK + s * kA1Tile) + off),
+                   idesc_qk, k != 0 ? 1u : 0u);
+      }
+      tc_commit(&s_full[b]);
+    };
+    mbar_wait(q_full, 0, 0xA20u);
+    issue_qk(0);
+    for (int j = 0; j < n_t; ++j) {
+      if (j + 1 < n_t) issue_qk(j + 1);
+      const int s = j % kA1Stages;
+      mbar_wait(p_full, (uint32_t)j & 1u, 0xA30u);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < kA1BN / 16; ++k) {
+        const uint32_t offp = (uint32_t)(k >> 2) * kA1Half + (uint32_t)(k & 3) * 32u;  // P: K-major over keys
+        const uint32_t offv = (uint32_t)k * 16u * 128u;                                 // V: 16 key rows of 128 B
+        tc_mma_f16(tO, make_smem_desc_sw128(smem_u32(sP) + offp),
+                   make_smem_desc_sw128_mn(smem_u32(sV + s * kA1Tile) + offv, kA1Half), idesc_pv, (j | k) != 0 ? 1u : 0u);
+      }
+      tc_commit(pv_done);
+      tc_commit(&kv_empty[s]);
+    }
+  } else if (warp >= 2) {
+    // ------------------------------ softmax + epilogue ------------------------
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int ch = (warp - 2) >> 2;       // which 64-key half of the row this thread handles
+    const int row = quad * 32 + lane;     // query row inside the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const uint32_t col_off = (uint32_t)(ch * 64);
+    const int qpos = p.q_pos0 + q0 + row;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    float m_used = -INFINITY;  // row maximum the exponentials are currently taken against (raw score units)
+    float l_run = 0.f;         // this thread's share of the row sum
+    for (int j = 0; j < n_t; ++j) {
+      const int b = j & 1;
+      mbar_wait(&s_full[b], ((uint32_t)(j >> 1)) & 1u, 0xB00u + b);
+      tc_fence_after();
+      uint32_t sv[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        tmem_ld_32x32(tS[b] + lane_off + col_off + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[b]);
+      // mask (causal and past-the-end keys) and row maximum
+      const int k0 = j * kA1BN + ch * 64;
+      const bool need_mask = (j * kA1BN + kA1BN - 1 > p.q_pos0 + q0) || (j * kA1BN + kA1BN > total_kv);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        float v = __uint_as_float(sv[c]);
+        if (need_mask && (k0 + c > qpos || k0 + c >= total_kv)) v = -INFINITY;
+        sv[c] = __float_as_uint(v);
+        mx = fmaxf(mx, v);
+      }
+      s_mx[b][ch][row] = mx;
+      named_bar_sync(2, 256);
+      mx = fmaxf(mx, s_mx[b][ch ^ 1][row]);
+      // P smem and the O accumulator are only touched once the previous tile's P V has retired
+      if (j > 0) mbar_wait(pv_done, ((uint32_t)(j - 1)) & 1u, 0xB10u);
+      // lazy rescale: keep exponentiating against m_used until the row maximum has grown by > 2^8
+      const bool grow = (mx > m_used + 8.0f / sl2) || (m_used == -INFINITY && mx != -INFINITY);
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = fmaxf(m_used, mx);
+        const float corr = (m_used == -INFINITY) ? 0.f : exp2f((m_used - m_new) * sl2);
+        l_run *= corr;
+        if (j > 0) {
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32(tO + lane_off + col_off + (uint32_t)(c * 32), ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * corr);
+            tmem_st_32x32(tO + lane_off + col_off + (uint32_t)(c * 32), ov);
+          }
+          tmem_st_wait();
+        }
+        m_used = m_new;
+      }
+      const float m_off = (m_used == -INFINITY) ? 0.f : m_used * sl2;
+      float rs = 0.f;
+      uint8_t* prow = sP + (size_t)ch * kA1Half + (size_t)row * 128;  // keys [ch*64, ch*64+64) = P half `ch`
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {  // 16-byte chunks of 8 keys
+        float pv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          pv[e] = exp2f(__uint_as_float(sv[c8 * 8 + e]) * sl2 - m_off);
+          rs += pv[e];
+        }
+        uint4 o;
+        o.x = pack_bf16(pv[0], pv[1]);
+        o.y = pack_bf16(pv[2], pv[3]);
+        o.z = pack_bf16(pv[4], pv[5]);
+        o.w = pack_bf16(pv[6], pv[7]);
+        *reinterpret_cast<uint4*>(prow + ((c8 ^ (row & 7)) << 4)) = o;
+      }
+      l_run += rs;
+      fence_proxy_async();  // P was written by the generic proxy; the MMA reads it through the async proxy
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16 -> global (two threads share one 256-byte output row)
+    s_lsum[ch][row] = l_run;
+    named_bar_sync(2, 256);
+    const float l_tot = s_lsum[0][row] + s_lsum[1][row];
+    mbar_wait(pv_done, ((uint32_t)(n_t - 1)) & 1u, 0xB20u);
+    tc_fence_after();
+    const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+    const int qr = q0 + row;
+    __nv_bfloat16* dst = p.out + (int64_t)qr * (p.H * p.dh) + h * p.dh + ch * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t ov[32];
+      __syncwarp();
+      tmem_ld_32x32(tO + lane_off + col_off + (uint32_t)(c * 32), ov);
+      tmem_ld_wait();
+      if (qr < p.n_q && ch * 64 + c * 32 < p.dh) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(ov[e + 0]) * inv, __uint_as_float(ov[e + 1]) * inv);
+          o.y = pack_bf16(__uint_as_float(ov[e + 2]) * inv, __uint_as_float(ov[e + 3]) * inv);
+          o.z = pack_bf16(__uint_as_float(ov[e + 4]) * inv, __uint_as_float(ov[e + 5]) * inv);
+          o.w = pack_bf16(__uint_as_float(ov[e + 6]) * inv, __uint_as_float(ov[e + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 32 + e) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace advspec

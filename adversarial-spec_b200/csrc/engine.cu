@@ -39,6 +39,7 @@
 #include "attn.cuh"
 #include "attn_decode_mma.cuh"
 #include "attn_prefill_tc.cuh"
+#include "attn_prefill_tc_v1.cuh"
 #include "common.cuh"
 #include "decode_kernels.cuh"
 #include "gemm_tcgen05.cuh"
@@ -258,7 +259,9 @@ void gemm_schedule(GemmParams* p, int BN, int epi, int grid, unsigned int* sem) 
   const int tail = tiles % grid;
   if (g_gemm_splitk && sem && (epi == EPI_RESADD_F32 || epi == EPI_F32) && tiles > grid && tail > 0 &&
       tail <= kGemmSemWords) {
-    const int split = std::min(std::min(grid / tail, 4), num_kb / 8);
+    // a split must keep a long K loop (>= 48 k-blocks = 3,072 columns): shorter items are all pipeline fill and
+    // drain plus serialised epilogues (measured: the o-proj, K = 4,096, went from 167 to 207 us with 21-block splits)
+    const int split = std::min(std::min(grid / tail, 4), num_kb / 48);
     if (split >= 2) {
       p->full_items = tiles - tail;
       p->split = split;
@@ -285,6 +288,7 @@ cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, GemmPara
 
 bool g_gemm_narrow = false;  // ADVSPEC_GEMM_NARROW=1 (experiment)
 bool g_attn_prefill_tc = true;  // ADVSPEC_ATTN_PREFILL_TC=0 falls back to the mma.sync kernel (A/B)
+bool g_attn_prefill_v1 = false; // ADVSPEC_ATTN_PREFILL_TC=1: the round-1 tcgen05 pipeline (A/B)
 
 // C = A[M,K] * B[N,K]^T on tcgen05.  A rows / B rows are the TMA extents.
 cudaError_t launch_gemm(const void* A, int64_t lda, int64_t a_rows, const void* B, int64_t ldb,
@@ -482,13 +486,19 @@ cudaError_t launch_attn_prefill_tc(const void* q, int64_t ldq, const void* kc, c
     if (err) *err = "cuTensorMapEncodeTiled failed (attention)";
     return cudaErrorInvalidValue;
   }
+  AttnPrefillTcParams p{reinterpret_cast<__nv_bfloat16*>(out), n_q, q_pos0, H, Hkv, (int)kv_stride,
+                        1.0f / sqrtf((float)dh), dh};
+  dim3 grid((n_q + kAtBM - 1) / kAtBM, H);
+  if (g_attn_prefill_v1) {  // ADVSPEC_ATTN_PREFILL_TC=1: round-1 pipeline (A/B)
+    cudaError_t e = set_smem(attn_prefill_tc_v1_kernel, kA1Smem);
+    if (e != cudaSuccess) return e;
+    attn_prefill_tc_v1_kernel<<<grid, kA1Threads, kA1Smem, st>>>(tq, tk, tv, p);
+    return cudaGetLastError();
+  }
   {  // function attributes are per device: set on every launch (host-side, microseconds)
     cudaError_t e = set_smem(attn_prefill_tc_kernel, kAtSmem);
     if (e != cudaSuccess) return e;
   }
-  AttnPrefillTcParams p{reinterpret_cast<__nv_bfloat16*>(out), n_q, q_pos0, H, Hkv, (int)kv_stride,
-                        1.0f / sqrtf((float)dh), dh};
-  dim3 grid((n_q + kAtBM - 1) / kAtBM, H);
   attn_prefill_tc_kernel<<<grid, kAtThreads, kAtSmem, st>>>(tq, tk, tv, p);
   return cudaGetLastError();
 }
@@ -1208,6 +1218,7 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   g_gemm_splitk = gs ? atoi(gs) != 0 : 1;
   const char* tc = getenv("ADVSPEC_ATTN_PREFILL_TC");
   g_attn_prefill_tc = tc ? atoi(tc) != 0 : true;
+  g_attn_prefill_v1 = tc && atoi(tc) == 1;
   const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT");
   g_attn_min_split = ms ? std::max(64, atoi(ms)) : 256;
 
@@ -1218,6 +1229,11 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
       const char* ef = getenv("ADVSPEC_L2_EVICT_FIRST");
       const int v = ef ? atoi(ef) : 1;
       E_CUDA(e, cudaMemcpyToSymbol(g_l2_evict_first, &v, sizeof v));
+    }
+    {
+      const char* ap = getenv("ADVSPEC_ATTN_POLY");
+      const int v = ap ? atoi(ap) : 1;
+      E_CUDA(e, cudaMemcpyToSymbol(g_attn_poly, &v, sizeof v));
     }
     E_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     E_CUDA(e, cudaEventCreate(&e->ev0));
