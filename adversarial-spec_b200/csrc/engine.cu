@@ -39,7 +39,6 @@
 #include "attn.cuh"
 #include "attn_decode_mma.cuh"
 #include "attn_prefill_tc.cuh"
-#include "attn_prefill_tc_v1.cuh"
 #include "common.cuh"
 #include "decode_kernels.cuh"
 #include "gemm_tcgen05.cuh"
@@ -234,7 +233,8 @@ cudaError_t set_smem(K kernel, int bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-int g_gemm_band_mb = 48;   // ADVSPEC_GEMM_BAND_MB: A-operand bytes of one raster band (0 = one band, the old walk)
+int g_gemm_band_mb = 0;    // ADVSPEC_GEMM_BAND_MB=<n>: raster bands whose A rows total n MB (0 = one band; measured: 48 MB
+                           // bands cut the down-proj's DRAM reads from 963 to 864 MB but not its time)
 int g_gemm_splitk = 1;     // ADVSPEC_GEMM_SPLITK=0 turns the K-split of the last partial wave off
 constexpr int kGemmSemWords = 256;  // ordering words a caller provides for the K-split tail
 
@@ -288,7 +288,6 @@ cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, GemmPara
 
 bool g_gemm_narrow = false;  // ADVSPEC_GEMM_NARROW=1 (experiment)
 bool g_attn_prefill_tc = true;  // ADVSPEC_ATTN_PREFILL_TC=0 falls back to the mma.sync kernel (A/B)
-bool g_attn_prefill_v1 = false; // ADVSPEC_ATTN_PREFILL_TC=1: the round-1 tcgen05 pipeline (A/B)
 
 // C = A[M,K] * B[N,K]^T on tcgen05.  A rows / B rows are the TMA extents.
 cudaError_t launch_gemm(const void* A, int64_t lda, int64_t a_rows, const void* B, int64_t ldb,
@@ -489,12 +488,6 @@ cudaError_t launch_attn_prefill_tc(const void* q, int64_t ldq, const void* kc, c
   AttnPrefillTcParams p{reinterpret_cast<__nv_bfloat16*>(out), n_q, q_pos0, H, Hkv, (int)kv_stride,
                         1.0f / sqrtf((float)dh), dh};
   dim3 grid((n_q + kAtBM - 1) / kAtBM, H);
-  if (g_attn_prefill_v1) {  // ADVSPEC_ATTN_PREFILL_TC=1: round-1 pipeline (A/B)
-    cudaError_t e = set_smem(attn_prefill_tc_v1_kernel, kA1Smem);
-    if (e != cudaSuccess) return e;
-    attn_prefill_tc_v1_kernel<<<grid, kA1Threads, kA1Smem, st>>>(tq, tk, tv, p);
-    return cudaGetLastError();
-  }
   {  // function attributes are per device: set on every launch (host-side, microseconds)
     cudaError_t e = set_smem(attn_prefill_tc_kernel, kAtSmem);
     if (e != cudaSuccess) return e;
@@ -1213,12 +1206,11 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   g_x_smem_max = xm ? (size_t)atoll(xm) : 40000;
   g_gemm_narrow = getenv("ADVSPEC_GEMM_NARROW") != nullptr;
   const char* gb = getenv("ADVSPEC_GEMM_BAND_MB");
-  g_gemm_band_mb = gb ? std::max(0, atoi(gb)) : 48;
+  g_gemm_band_mb = gb ? std::max(0, atoi(gb)) : 0;
   const char* gs = getenv("ADVSPEC_GEMM_SPLITK");
   g_gemm_splitk = gs ? atoi(gs) != 0 : 1;
   const char* tc = getenv("ADVSPEC_ATTN_PREFILL_TC");
   g_attn_prefill_tc = tc ? atoi(tc) != 0 : true;
-  g_attn_prefill_v1 = tc && atoi(tc) == 1;
   const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT");
   g_attn_min_split = ms ? std::max(64, atoi(ms)) : 256;
 
@@ -1229,11 +1221,6 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
       const char* ef = getenv("ADVSPEC_L2_EVICT_FIRST");
       const int v = ef ? atoi(ef) : 1;
       E_CUDA(e, cudaMemcpyToSymbol(g_l2_evict_first, &v, sizeof v));
-    }
-    {
-      const char* ap = getenv("ADVSPEC_ATTN_POLY");
-      const int v = ap ? atoi(ap) : 1;
-      E_CUDA(e, cudaMemcpyToSymbol(g_attn_poly, &v, sizeof v));
     }
     E_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     E_CUDA(e, cudaEventCreate(&e->ev0));
@@ -2041,7 +2028,7 @@ advspec_status advspec_op_gemm(int32_t device, const void* A, int64_t lda, const
   std::string why;
   {  // the A/B knobs are re-read per call (unset = default)
     const char* gb = getenv("ADVSPEC_GEMM_BAND_MB");
-    g_gemm_band_mb = gb ? std::max(0, atoi(gb)) : 48;
+    g_gemm_band_mb = gb ? std::max(0, atoi(gb)) : 0;
     const char* gs = getenv("ADVSPEC_GEMM_SPLITK");
     g_gemm_splitk = gs ? atoi(gs) != 0 : 1;
   }

@@ -285,7 +285,7 @@ def test_eos_stops_one_opponent_only(cuda_device):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [{"ADVSPEC_L2_EVICT_FIRST": "0"}, {"ADVSPEC_NO_PDL": "1"}, {"ADVSPEC_ATTN_IMPL": "1"},
-                                 {"ADVSPEC_GEMV_IMPL": "1"}, {"ADVSPEC_GEMM_SPLITK": "0", "ADVSPEC_GEMM_BAND_MB": "0"}])
+                                 {"ADVSPEC_GEMV_IMPL": "1"}, {"ADVSPEC_GEMM_SPLITK": "0", "ADVSPEC_GEMM_BAND_MB": "48"}])
 def test_opt_in_decode_variants_give_the_default_logits(cuda_device, diag, monkeypatch, env):
     """The A/B knobs of DESIGN.md §4 (L2 policy, no programmatic launch, the scalar decode attention, the
     register-load GEMV, the prefill GEMM's plain tile walk) change scheduling, not arithmetic: teacher-forced decode logits must match

@@ -113,8 +113,9 @@ def test_gemv(cuda_device, diag, N, K, b, mode):
 @pytest.mark.parametrize("M,N,K,epi", [(5068, 4096, 14336, 1), (5068, 4096, 4096, 3), (2100, 3584, 18944, 1),
                                        (9000, 8192, 3584, 1)])
 def test_gemm_k_split_tail_is_deterministic_and_schedule_independent(cuda_device, diag, monkeypatch, M, N, K, epi):
-    """The K-split of the last partial wave adds its partial tiles in split order: two runs give the same
-    bits, and the result differs from the unsplit, single-band schedule only by fp32 summation order."""
+    """The K-split of the last partial wave (long K only) adds its partial tiles in split order: two runs give
+    the same bits, the banded raster gives the same bits, and the unsplit schedule differs only by fp32
+    summation order."""
     lib = eng.load_library()
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
@@ -130,10 +131,12 @@ def test_gemm_k_split_tail_is_deterministic_and_schedule_independent(cuda_device
     a, b = run(), run()
     assert torch.equal(a, b), "same schedule, same bits"
     monkeypatch.setenv("ADVSPEC_GEMM_SPLITK", "0")
-    monkeypatch.setenv("ADVSPEC_GEMM_BAND_MB", "0")
     plain = run()
     monkeypatch.delenv("ADVSPEC_GEMM_SPLITK")
+    monkeypatch.setenv("ADVSPEC_GEMM_BAND_MB", "48")
+    banded = run()
     monkeypatch.delenv("ADVSPEC_GEMM_BAND_MB")
+    assert torch.equal(banded, a), "the raster order does not change any tile's arithmetic"
     run()  # restores the defaults inside the library (the knobs are re-read per call)
     ref = A.float() @ B.float().T + (C0 if epi == 1 else 0)
     scale = float(ref.abs().max())
