@@ -36,9 +36,13 @@ def test_tensor_parallel_matches_hf_and_the_unsplit_engine(world):
     # TP=2 is 32 query / 4 KV heads and 14,336 MLP columns
     for name in ("tiny-gqa4", "tiny-llama-128", "llama-3-70b-2layer-v32k"):
         r = res[name]
-        # same tolerance as the single-GPU parity tests (tests/test_gpu_engine.py): bf16 activations
-        assert r["prefill_max_over_std"] < 0.08 and r["prefill_rms_over_std"] < 0.02, r
-        assert r["decode_max_over_std"] < 0.08, r
+        # same tolerance as the single-GPU parity tests (tests/test_gpu_engine.py): bf16 activations.  The
+        # 70B-shaped case compares 200 positions x 32,768 logits = 6.5 M values: the largest of that many errors
+        # of rms r sits near r * sqrt(2 ln n) = 5.6 r, so its maximum is bounded at 6 x the rms tolerance
+        # (measured: rms 0.016, max 0.090; oracle/restate.py with the engine's rounding points predicts the same)
+        tol_max = 0.12 if name.startswith("llama-3-70b") else 0.08
+        assert r["prefill_max_over_std"] < tol_max and r["prefill_rms_over_std"] < 0.02, r
+        assert r["decode_max_over_std"] < tol_max, r
         assert r["ranks_identical"], r
         # the all-reduce changes the summation order, so a near-tie may flip a token; most must agree
         assert r["greedy_token_agreement"] >= 0.75 and r["sampled_token_agreement"] >= 0.5, r
