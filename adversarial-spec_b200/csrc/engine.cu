@@ -39,7 +39,6 @@
 #include "attn.cuh"
 #include "attn_decode_mma.cuh"
 #include "attn_prefill_tc.cuh"
-#include "attn_prefill_tc64.cuh"
 #include "common.cuh"
 #include "decode_kernels.cuh"
 #include "gemm_tcgen05.cuh"
@@ -289,7 +288,6 @@ cudaError_t launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, GemmPara
 
 bool g_gemm_narrow = false;  // ADVSPEC_GEMM_NARROW=1 (experiment)
 bool g_attn_prefill_tc = true;  // ADVSPEC_ATTN_PREFILL_TC=0 falls back to the mma.sync kernel (A/B)
-bool g_attn_prefill_64 = true;  // ADVSPEC_ATTN_PREFILL_TC=1: 128-key tiles, one CTA per SM; default (2): 64-key tiles, two
 
 // C = A[M,K] * B[N,K]^T on tcgen05.  A rows / B rows are the TMA extents.
 cudaError_t launch_gemm(const void* A, int64_t lda, int64_t a_rows, const void* B, int64_t ldb,
@@ -490,17 +488,6 @@ cudaError_t launch_attn_prefill_tc(const void* q, int64_t ldq, const void* kc, c
   AttnPrefillTcParams p{reinterpret_cast<__nv_bfloat16*>(out), n_q, q_pos0, H, Hkv, (int)kv_stride,
                         1.0f / sqrtf((float)dh), dh};
   dim3 grid((n_q + kAtBM - 1) / kAtBM, H);
-  if (g_attn_prefill_64) {  // 64-key tiles, two CTAs per SM (attn_prefill_tc64.cuh)
-    CUtensorMap tk6, tv6;
-    if (!make_tmap(&tk6, kc, kv_rows, dh, dh, 64) || !make_tmap(&tv6, vc, kv_rows, dh, dh, 64)) {
-      if (err) *err = "cuTensorMapEncodeTiled failed (attention, 64-key tiles)";
-      return cudaErrorInvalidValue;
-    }
-    cudaError_t e = set_smem(attn_prefill_tc64_kernel, kA6Smem);
-    if (e != cudaSuccess) return e;
-    attn_prefill_tc64_kernel<<<grid, kA6Threads, kA6Smem, st>>>(tq, tk6, tv6, p);
-    return cudaGetLastError();
-  }
   {  // function attributes are per device: set on every launch (host-side, microseconds)
     cudaError_t e = set_smem(attn_prefill_tc_kernel, kAtSmem);
     if (e != cudaSuccess) return e;
@@ -1224,7 +1211,6 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   g_gemm_splitk = gs ? atoi(gs) != 0 : 1;
   const char* tc = getenv("ADVSPEC_ATTN_PREFILL_TC");
   g_attn_prefill_tc = tc ? atoi(tc) != 0 : true;
-  g_attn_prefill_64 = !(tc && atoi(tc) == 1);
   const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT");
   g_attn_min_split = ms ? std::max(64, atoi(ms)) : 256;
 
@@ -2092,8 +2078,7 @@ advspec_status advspec_op_gemv(int32_t device, const void* W, const void* x, con
   {
     const char* tc = getenv("ADVSPEC_ATTN_PREFILL_TC");
     g_attn_prefill_tc = tc ? atoi(tc) != 0 : true;
-    g_attn_prefill_64 = !(tc && atoi(tc) == 1);
-  }
+    }
   if (const char* ms = getenv("ADVSPEC_ATTN_MIN_SPLIT")) g_attn_min_split = std::max(64, atoi(ms));
   cudaError_t r = launch_gemv(p, b, device, 0, false);
   if (r != cudaSuccess) {
