@@ -58,6 +58,14 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, 
   return d;
 }
 
+// One MUFU.EX2 (exp2f() adds a range test and two scalings per element for denormal results, which a
+// probability that is about to be rounded to bf16 does not need; -inf -> 0).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnPrefillTcParams {
   __nv_bfloat16* out;  // [n_q][H*dh]
   int n_q, q_pos0, H, Hkv;
@@ -203,14 +211,17 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       // mask (causal and past-the-end keys) and row maximum
       const int k0 = j * kAtBN + ch * 64;
       const bool need_mask = (j * kAtBN + kAtBN - 1 > p.q_pos0 + q0) || (j * kAtBN + kAtBN > total_kv);
+      // The softmax warps are issue-bound (ncu: scheduler slots 66 % active, tensor pipe 28-32 %): keep the
+      // per-element instruction count down.  The causal / past-the-end mask only exists on the diagonal and
+      // last tiles — a CTA-uniform branch, not a select per element on every tile.
+      if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (k0 + c > qpos || k0 + c >= total_kv) sv[c] = 0xff800000u;  // -inf
+      }
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float v = __uint_as_float(sv[c]);
-        if (need_mask && (k0 + c > qpos || k0 + c >= total_kv)) v = -INFINITY;
-        sv[c] = __float_as_uint(v);
-        mx = fmaxf(mx, v);
-      }
+      for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
       s_mx[b][ch][row] = mx;
       named_bar_sync(2, 256);
       mx = fmaxf(mx, s_mx[b][ch ^ 1][row]);
@@ -245,7 +256,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         float pv[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          pv[e] = exp2f(__uint_as_float(sv[c8 * 8 + e]) * sl2 - m_off);
+          pv[e] = ex2_approx(fmaf(__uint_as_float(sv[c8 * 8 + e]), sl2, -m_off));
           rs += pv[e];
         }
         uint4 o;
