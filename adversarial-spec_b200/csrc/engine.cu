@@ -480,8 +480,8 @@ cudaError_t launch_attn_prefill_tc(const void* q, int64_t ldq, const void* kc, c
   CUtensorMap tq, tk, tv;
   const int64_t kv_rows = (int64_t)Hkv * kv_stride;
   // the Q map spans the whole row (ldq columns): the second 64-column box of the last head may reach into K's columns
-  if (!make_tmap(&tq, q, n_q, ldq, ldq, 128) || !make_tmap(&tk, kc, kv_rows, dh, dh, 128) ||
-      !make_tmap(&tv, vc, kv_rows, dh, dh, 128)) {
+  if (!make_tmap(&tq, q, n_q, ldq, ldq, kAtBM) || !make_tmap(&tk, kc, kv_rows, dh, dh, kAtBN) ||
+      !make_tmap(&tv, vc, kv_rows, dh, dh, kAtBN)) {
     if (err) *err = "cuTensorMapEncodeTiled failed (attention)";
     return cudaErrorInvalidValue;
   }
@@ -490,6 +490,10 @@ cudaError_t launch_attn_prefill_tc(const void* q, int64_t ldq, const void* kc, c
   dim3 grid((n_q + kAtBM - 1) / kAtBM, H);
   {  // function attributes are per device: set on every launch (host-side, microseconds)
     cudaError_t e = set_smem(attn_prefill_tc_kernel, kAtSmem);
+    if (e != cudaSuccess) return e;
+    // two CTAs per SM need the whole shared-memory carve-out (the default heuristic sizes it for ONE block)
+    e = cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
   }
   attn_prefill_tc_kernel<<<grid, kAtThreads, kAtSmem, st>>>(tq, tk, tv, p);
