@@ -173,13 +173,13 @@ __global__ void __launch_bounds__(BM * 2) attn_prefill_kernel(AttnPrefillParams 
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       const float m_new = fmaxf(m_run[i], mx);
       const float m_off = (m_new == -INFINITY) ? 0.f : m_new * sl2;
-      const float corr = (m_run[i] == -INFINITY) ? 0.f : exp2f(m_run[i] * sl2 - m_off);
+      const float corr = (m_run[i] == -INFINITY) ? 0.f : ex2_approx(m_run[i] * sl2 - m_off);
       m_run[i] = m_new;
       float rs = 0.f;
 #pragma unroll
       for (int nb = 0; nb < BN / 8; ++nb) {
-        const float p0 = exp2f(s[nb][2 * i] * sl2 - m_off);
-        const float p1 = exp2f(s[nb][2 * i + 1] * sl2 - m_off);
+        const float p0 = ex2_approx(fmaf(s[nb][2 * i], sl2, -m_off));
+        const float p1 = ex2_approx(fmaf(s[nb][2 * i + 1], sl2, -m_off));
         s[nb][2 * i] = p0;
         s[nb][2 * i + 1] = p1;
         rs += p0 + p1;

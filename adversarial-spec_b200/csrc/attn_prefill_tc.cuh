@@ -58,14 +58,6 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, 
   return d;
 }
 
-// One MUFU.EX2 (exp2f() adds a range test and two scalings per element for denormal results, which a
-// probability that is about to be rounded to bf16 does not need; -inf -> 0).
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 struct AttnPrefillTcParams {
   __nv_bfloat16* out;  // [n_q][H*dh]
   int n_q, q_pos0, H, Hkv;

@@ -34,6 +34,14 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   return r;
 }
 
+// One MUFU.EX2 (exp2f() adds a range test and two scalings per element for denormal results, which a
+// probability that is about to be rounded to bf16 does not need; -inf -> 0).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
