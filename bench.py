@@ -198,11 +198,13 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_sample(args, system_prompt, user_message, sample_layers, sample_gen):
+def cpu_sample(args, system_prompt, user_message, sample_layers, sample_gen, prompt_frac=1.0):
     """One bounded sample of the reference's CPU fan-out; returns (estimated full-workload seconds, raw
-    sample seconds, description).  The sample keeps the FULL prompt and the layer shape but runs
-    `sample_layers` of the model's layers and `sample_gen` new tokens; per-layer time (forward hooks) is
-    scaled to all layers, per-token decode time to `args.gen` tokens."""
+    sample seconds, description).  The sample keeps the layer shape but runs `sample_layers` of the model's
+    layers and `sample_gen` new tokens; per-layer time (forward hooks) is scaled to all layers, per-token decode
+    time to `args.gen` tokens.  `prompt_frac` < 1 (reference arm only, when even one layer of the full prompt
+    does not fit a step's share of the budget) prefills a leading slice of the prompt and scales the prefill by
+    the per-layer flop ratio of SURVEY.md §8(d) (linear GEMM term + quadratic attention term)."""
     import advspec_loader
 
     advspec_loader.load()
@@ -217,10 +219,13 @@ def cpu_sample(args, system_prompt, user_message, sample_layers, sample_gen):
     saved = os.environ.get("ADVSPEC_MAX_NEW_TOKENS")
     os.environ["ADVSPEC_MAX_NEW_TOKENS"] = str(sample_gen)
     os.environ["ADVSPEC_CPU_FAST_INIT"] = "1"
+    user = user_message
+    if prompt_frac < 1.0:
+        user = user_message[: max(64, int(len(user_message) * prompt_frac))]
     try:
         fanout_ref.take_timings()
         t0 = time.perf_counter()
-        fanout_ref.cpu_call_models_parallel([f"local/{name}"] * args.opponents, system_prompt, user_message)
+        fanout_ref.cpu_call_models_parallel([f"local/{name}"] * args.opponents, system_prompt, user)
         wall = time.perf_counter() - t0
         tm = fanout_ref.take_timings()
     finally:
@@ -236,10 +241,19 @@ def cpu_sample(args, system_prompt, user_message, sample_layers, sample_gen):
     dec_layer = sum(t["decode_layer_s"] for t in tm) / n
     new_tok = sum(t["new_tokens"] for t in tm) / n
     est_prefill = pre_wall + (scale - 1.0) * pre_layer
+    sliced = ""
+    if prompt_frac < 1.0:
+        p_s = tm[0]["prompt_tokens"]
+        p_full = len(_prompt_ids(full, system_prompt, user_message))
+        one = model_spec.with_layers(full, 1, "flops-1layer")
+        per_layer = lambda t: one.prefill_flops(t) - 2.0 * one.vocab_size * one.d_model
+        ratio = per_layer(p_full) / per_layer(p_s)
+        est_prefill *= ratio
+        sliced = f"; prompt slice {p_s} of {p_full} tokens, prefill x{ratio:.2f} by per-layer flops"
     est_decode = (dec_wall + (scale - 1.0) * dec_layer) * (args.gen / max(new_tok, 1.0))
-    desc = (f"{args.opponents} threads x HF CPU fp32 {name}: full {tm[0]['prompt_tokens']}-token prompt, "
+    desc = (f"{args.opponents} threads x HF CPU fp32 {name}: {tm[0]['prompt_tokens']}-token prompt, "
             f"{int(new_tok)} new tokens, {layers} of {full.n_layers} layers; layer time x{scale:.0f}, "
-            f"decode x{args.gen / max(new_tok, 1.0):.0f} to the full workload")
+            f"decode x{args.gen / max(new_tok, 1.0):.0f} to the full workload{sliced}")
     return est_prefill + est_decode, wall, desc
 
 
@@ -276,21 +290,26 @@ def run_reference_arm(args, rank, world):
     n_panels = world if world > 1 else max(args.gpus, 1)
     n_samples = max(1, args.warmup) + args.steps
     share = args.cpu_budget_s / n_samples
-    # calibration: the cheapest sample first (1 layer, 2 new tokens; builds the model), then the largest of
-    # {1, 2 layers} x {2, 16 tokens} whose wall time fits a step's share of the budget
+    # calibration: the cheapest full-prompt sample first (1 layer, 2 new tokens; builds the model), then the
+    # largest of {1, 2 layers} x {2, 16 tokens} whose wall time fits a step's share of the budget; if even the
+    # cheapest does not fit, a leading slice of the prompt
     t0 = time.perf_counter()
     est, wall, desc = cpu_sample(args, system_prompt, user_message, 1, 2)
     first_wall = time.perf_counter() - t0
     est, wall, desc = cpu_sample(args, system_prompt, user_message, 1, 2)
+    frac = 1.0
     layers = min(args.cpu_sample_layers, 2) if 2.2 * wall <= share else 1
     gen = args.cpu_sample_gen if 1.3 * wall * layers <= share else 2
-    if (layers, gen) != (1, 2):
+    if wall > share:
+        frac = max(0.1, 0.8 * share / wall)
+        est, wall, desc = cpu_sample(args, system_prompt, user_message, 1, 2, frac)
+    elif (layers, gen) != (1, 2):
         est, wall, desc = cpu_sample(args, system_prompt, user_message, layers, gen)  # (builds the 2-layer model)
     for _ in range(max(0, args.warmup - 2)):
-        cpu_sample(args, system_prompt, user_message, layers, gen)
+        cpu_sample(args, system_prompt, user_message, layers, gen, frac)
     ests, walls = [], []
     for _ in range(args.steps):
-        est, wall, desc = cpu_sample(args, system_prompt, user_message, layers, gen)
+        est, wall, desc = cpu_sample(args, system_prompt, user_message, layers, gen, frac)
         ests.append(est)
         walls.append(wall)
     vals = sorted(args.opponents * args.gen / e for e in ests)
@@ -699,10 +718,11 @@ def run_b200_arm(args, rank, world, local_rank):
         wall = time.perf_counter() - t0
         launches = engine().timing().kernel_launches - launches0
         clocks = sampler.stop()
-        prefilled = runtime.PREFIXES.stats["tokens_prefilled"] - pf0["tokens_prefilled"]
-        if prefilled != args.steps * prompt_tokens:
-            raise SystemExit(f"bench.py: {prefilled} prompt tokens were prefilled in the timed region, expected "
-                             f"{args.steps * prompt_tokens} (a step must not reuse the previous step's prefix)")
+        pf1 = runtime.PREFIXES.stats
+        reused = (pf1["extended"] - pf0["extended"]) + (pf1["rearmed"] - pf0["rearmed"])
+        if reused or pf1["full"] - pf0["full"] != args.steps:
+            raise SystemExit(f"bench.py: {reused} of the {args.steps} timed steps reused the previous step's prefix "
+                             f"(every step must prefill its whole prompt)")
 
     # max over ranks of the time, sum over ranks of the tokens
     (dev_ms, wall), (out_tokens, launches) = runtime.reduce_round_stats([dev_ms, wall], [out_tokens, launches],
