@@ -250,10 +250,12 @@ def cpu_sample(args, system_prompt, user_message, sample_layers, sample_gen, pro
         ratio = per_layer(p_full) / per_layer(p_s)
         est_prefill *= ratio
         sliced = f"; prompt slice {p_s} of {p_full} tokens, prefill x{ratio:.2f} by per-layer flops"
-    est_decode = (dec_wall + (scale - 1.0) * dec_layer) * (args.gen / max(new_tok, 1.0))
+    # n new tokens cost n-1 decode forwards (the first comes from the prefill's logits)
+    fwd = max(new_tok - 1.0, 1.0)
+    est_decode = (dec_wall + (scale - 1.0) * dec_layer) * ((args.gen - 1) / fwd)
     desc = (f"{args.opponents} threads x HF CPU fp32 {name}: {tm[0]['prompt_tokens']}-token prompt, "
-            f"{int(new_tok)} new tokens, {layers} of {full.n_layers} layers; layer time x{scale:.0f}, "
-            f"decode x{args.gen / max(new_tok, 1.0):.0f} to the full workload{sliced}")
+            f"{int(new_tok)} new tokens ({int(fwd)} decode forwards), {layers} of {full.n_layers} layers; layer time "
+            f"x{scale:.0f}, decode forwards x{(args.gen - 1) / fwd:.0f} to the full workload{sliced}")
     return est_prefill + est_decode, wall, desc
 
 
