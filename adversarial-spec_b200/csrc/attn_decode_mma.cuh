@@ -30,8 +30,9 @@ struct AttnDecode2Params {
   __nv_bfloat16* sk;         // suffix K [max_seqs][Hkv][sstride][DH] (this layer)
   __nv_bfloat16* sv;
   int64_t sstride;
-  const CUtensorMap* maps;   // [0] prefix K, [1] prefix V of this layer: 2-D (Hkv*pstride tokens) x DH,
-                             // box 64 tokens x 64 dims, 128-byte swizzle
+  CUtensorMap map_k, map_v;  // prefix K / V of this layer: 2-D (Hkv*pstride tokens) x DH, box 64 tokens x 64 dims,
+                             // 128-byte swizzle.  By value in the (grid-constant) parameter block: the TMA unit
+                             // then reads the descriptors from the constant bank instead of global memory
   const int* pos_b;          // [b] absolute position of each opponent's new token (device state)
   int slots[8];              // batch index -> opponent slot (fixed for the decode call)
   int prefix_len;
@@ -45,7 +46,7 @@ struct AttnDecode2Params {
 };
 
 template <int DH, int NST>
-__global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Params p) {
+__global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(const __grid_constant__ AttnDecode2Params p) {
   constexpr int BN = 64;
   constexpr int CPR = DH / 8;
   constexpr int TILE = BN * DH;  // elements of one K (or V) tile
@@ -100,9 +101,9 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
     for (int s = 0; s < NST; ++s) mbar_init(&full_bar[s], 1);
     fence_mbar_init();
   }
-  if (tid == 32) {  // the K/V tensor maps live in global memory: start fetching them before the first TMA needs them
-    tma_prefetch_desc(&p.maps[0]);
-    tma_prefetch_desc(&p.maps[1]);
+  if (tid == 32) {  // start fetching the K/V tensor maps before the first TMA needs them
+    tma_prefetch_desc(&p.map_k);
+    tma_prefetch_desc(&p.map_v);
   }
   __syncthreads();
 
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(AttnDecode2Para
         const int row0 = hk * (int)p.pstride + k0;
 #pragma unroll
         for (int h2 = 0; h2 < NH; ++h2) {
-          tma_load_2d(dK + h2 * HALF, &p.maps[0], &full_bar[st], h2 * 64, row0);
-          tma_load_2d(dV + h2 * HALF, &p.maps[1], &full_bar[st], h2 * 64, row0);
+          tma_load_2d(dK + h2 * HALF, &p.map_k, &full_bar[st], h2 * 64, row0);
+          tma_load_2d(dV + h2 * HALF, &p.map_v, &full_bar[st], h2 * 64, row0);
         }
       }
     } else {

@@ -589,7 +589,7 @@ struct advspec_engine {
   int a2_opg = 1, a2_n_og = 1, a2_n_splits = 1, a2_ctas = 0;
   int h_slots[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int* s_pos = nullptr;     // [max_seqs] absolute position of each batch entry's next token
-  CUtensorMap* kv_maps = nullptr;  // [L][2] device copies: prefix K / V tensor maps of each layer
+  std::vector<CUtensorMap> kv_maps;  // [L][2] prefix K / V tensor maps of each layer (passed by value per launch)
   bool attn_fused = false;  // this engine's shape is served by attn_decode_mma_kernel
 
   // opponent state (device arrays indexed by slot)
@@ -819,7 +819,7 @@ void free_all(advspec_engine* e) {
   if (e->ar_gen) cudaFree(e->ar_gen);
   void* ptrs[] = {e->w, e->inv_freq, e->rope_cos, e->rope_sin, e->pkv, e->skv, e->p_tokens, e->p_x,
                   e->p_xn, e->p_qkv, e->p_attn, e->p_h, e->prefill_logits, e->dx, e->dx_save, e->dq,
-                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->gemm_sem, e->items, e->s_pos, e->kv_maps,
+                  e->dlogits, e->dqkv, e->dattn, e->dh, e->part_m, e->part_l, e->part_o, e->gemm_sem, e->items, e->s_pos,
                   e->s_slots, e->s_forced, e->s_seeds, e->s_suf_len, e->s_n_out, e->s_done,
                   e->s_cur_tok, e->s_out, e->samp_pack};
   for (void* p : ptrs)
@@ -951,7 +951,8 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
       a2.sk = suffix_k(e, l);
       a2.sv = suffix_v(e, l);
       a2.sstride = d.max_new_tokens;
-      a2.maps = e->kv_maps + 2 * l;
+      a2.map_k = e->kv_maps[2 * l];
+      a2.map_v = e->kv_maps[2 * l + 1];
       a2.pos_b = e->s_pos;
       for (int i = 0; i < 8; ++i) a2.slots[i] = e->h_slots[i];
       a2.prefix_len = e->prefix_len;
@@ -1279,19 +1280,15 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
     e->attn_fused = g_attn_impl == 2 && (d.head_dim == 64 || d.head_dim == 96 || d.head_dim == 128 || d.head_dim == 256) && G <= 16 &&
                     d.n_heads <= 255;
     if (e->attn_fused) {
-      std::vector<CUtensorMap> hm((size_t)d.n_layers * 2);
+      e->kv_maps.resize((size_t)d.n_layers * 2);
       for (int l = 0; l < d.n_layers; ++l) {
         const int64_t rows = (int64_t)d.n_kv_heads * d.max_prefix_tokens;
-        if (!make_tmap(&hm[2 * l], prefix_k(e, l), rows, d.head_dim, d.head_dim, 64) ||
-            !make_tmap(&hm[2 * l + 1], prefix_v(e, l), rows, d.head_dim, d.head_dim, 64)) {
+        if (!make_tmap(&e->kv_maps[2 * l], prefix_k(e, l), rows, d.head_dim, d.head_dim, 64) ||
+            !make_tmap(&e->kv_maps[2 * l + 1], prefix_v(e, l), rows, d.head_dim, d.head_dim, 64)) {
           e->fail("cuTensorMapEncodeTiled failed for the prefix KV of layer %d", l);
           return ADVSPEC_ERR_CUDA;
         }
       }
-      E_CUDA(e, dmalloc(&e->kv_maps, hm.size()));
-      E_CUDA(e, cudaMemcpyAsync(e->kv_maps, hm.data(), hm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice,
-                                e->stream));
-      E_CUDA(e, cudaStreamSynchronize(e->stream));
     }
     E_CUDA(e, dmalloc(&e->s_slots, B));
     E_CUDA(e, dmalloc(&e->s_forced, B));
@@ -2151,19 +2148,16 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
     g_create_error = "op_attn_decode: cuTensorMapEncodeTiled failed";
     return ADVSPEC_ERR_CUDA;
   }
-  CUtensorMap* dmaps = nullptr;
   int* dpos = nullptr;
   float *pm = nullptr, *plv = nullptr, *po = nullptr;
   const size_t nrow = (size_t)b * n_heads * pl.n_slots;
   auto cleanup = [&]() {
-    cudaFree(dmaps);
     cudaFree(dpos);
     cudaFree(pm);
     cudaFree(plv);
     cudaFree(po);
   };
-  if (cudaMalloc(reinterpret_cast<void**>(&dmaps), sizeof hm) != cudaSuccess ||
-      cudaMalloc(reinterpret_cast<void**>(&dpos), 8 * sizeof(int)) != cudaSuccess ||
+  if (cudaMalloc(reinterpret_cast<void**>(&dpos), 8 * sizeof(int)) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&pm), nrow * 4) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&plv), nrow * 4) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&po), nrow * head_dim * 4) != cudaSuccess) {
@@ -2171,7 +2165,6 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
     g_create_error = "op_attn_decode: out of device memory";
     return ADVSPEC_ERR_OOM;
   }
-  cudaMemcpy(dmaps, hm, sizeof hm, cudaMemcpyHostToDevice);
   cudaMemcpy(dpos, pos_host, b * sizeof(int), cudaMemcpyHostToDevice);
   AttnDecode2Params a2{};
   a2.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
@@ -2183,7 +2176,8 @@ advspec_status advspec_op_attn_decode(int32_t device, const void* qkv, const voi
   a2.sk = reinterpret_cast<__nv_bfloat16*>(suffix_k);
   a2.sv = reinterpret_cast<__nv_bfloat16*>(suffix_v);
   a2.sstride = suffix_stride;
-  a2.maps = dmaps;
+  a2.map_k = hm[0];
+  a2.map_v = hm[1];
   a2.pos_b = dpos;
   for (int i = 0; i < 8; ++i) a2.slots[i] = i < b ? i : 0;
   a2.prefix_len = prefix_len;
