@@ -395,6 +395,7 @@ cudaError_t launch_gemv_v1(const GemvParams& p, int b, int device, cudaStream_t 
   return cudaErrorInvalidValue;
 }
 
+bool g_tp_ll = true;  // ADVSPEC_TP_AR=flag: the push / fence / flag / sum exchange instead of low-latency packets (A/B)
 int g_attn_min_split = 256;  // ADVSPEC_ATTN_MIN_SPLIT: fewest prefix tokens worth a split of their own
 size_t g_x_smem_max = 40000;  // ADVSPEC_X_SMEM_MAX: larger plain-bf16 inputs are read through L1 from global (measured faster)
 
@@ -723,7 +724,10 @@ advspec_status tp_allreduce(advspec_engine* e, float* buf, size_t count) {
     ap.rank = e->tp_rank;
     ap.max_elems = e->ar_max_elems;
     ap.gen = e->ar_gen;
-    E_CUDA(e, launch_pdl(tp_allreduce_kernel, dim3(kArCtas), dim3(kArThreads), 0, e->stream, true, ap));
+    if (g_tp_ll)
+      E_CUDA(e, launch_pdl(tp_allreduce_ll_kernel, dim3(kArCtas), dim3(kArThreads), 0, e->stream, true, ap));
+    else
+      E_CUDA(e, launch_pdl(tp_allreduce_kernel, dim3(kArCtas), dim3(kArThreads), 0, e->stream, true, ap));
     e->launches++;
     return ADVSPEC_OK;
   }
@@ -1210,6 +1214,10 @@ advspec_status advspec_engine_create(const advspec_model_desc* desc, int32_t dev
   const char* xm = getenv("ADVSPEC_X_SMEM_MAX");
   g_x_smem_max = xm ? (size_t)atoll(xm) : 40000;
   g_gemm_narrow = getenv("ADVSPEC_GEMM_NARROW") != nullptr;
+  {
+    const char* ar = getenv("ADVSPEC_TP_AR");
+    g_tp_ll = !(ar && std::string(ar) == "flag");
+  }
   const char* gb = getenv("ADVSPEC_GEMM_BAND_MB");
   g_gemm_band_mb = gb ? std::max(0, atoi(gb)) : 0;
   const char* gs = getenv("ADVSPEC_GEMM_SPLITK");
@@ -1408,7 +1416,8 @@ advspec_status advspec_tp_ipc_export(advspec_engine* e, uint8_t* out64) {
   E_CUDA(e, cudaSetDevice(e->device));
   if (!e->ar_region) {
     e->ar_max_elems = (int64_t)e->d.max_seqs * e->d.d_model;
-    const size_t bytes = kArFlagBytes + (size_t)2 * e->tp_size * e->ar_max_elems * sizeof(float);
+    // sized for the low-latency packets (8 bytes per float); the flag variant uses the first half
+    const size_t bytes = kArFlagBytes + (size_t)2 * e->tp_size * e->ar_max_elems * 2 * sizeof(float);
     E_CUDA(e, cudaMalloc(reinterpret_cast<void**>(&e->ar_region), bytes));
     E_CUDA(e, cudaMemset(e->ar_region, 0, bytes));
     E_CUDA(e, dmalloc(&e->ar_gen, kArCtas));
