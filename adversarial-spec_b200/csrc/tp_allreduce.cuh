@@ -7,6 +7,8 @@
 // CUDA IPC; NVSwitch gives all peers full bandwidth at once), raises a flag there, waits for the tp
 // flags in its own buffer and sums the tp slots in rank order — so every rank computes bit-identical
 // sums.  One launch of G CTAs; CTA i moves and reduces slice i only, so there is no grid-wide step.
+// (tp_allreduce_kernel below is this flag protocol, kept for A/B; the engine runs tp_allreduce_ll_kernel,
+// which carries the flag inside the data.)
 //
 // Layout of a rank's region:  flags u32 [2 sets][tp][kArCtas] (first kArFlagBytes), then
 // slots f32 [2 sets][tp][max_elems].  Two sets alternate by generation: a rank can be one exchange
