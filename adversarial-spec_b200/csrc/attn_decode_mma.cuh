@@ -97,15 +97,17 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(const __grid_co
   const int n_rows = is_prefix ? n_opp * p.G : p.G;
   const int slot_out = is_prefix ? j : p.n_splits;
 
-  if (tid == 0) {
-    for (int s = 0; s < NST; ++s) mbar_init(&full_bar[s], 1);
+  // The lane-0 thread of warp s owns ring stage s: it initialises the stage's barrier and (prefix items) issues
+  // the stage's first TMA at once — no CTA-wide barrier between kernel entry and the first load.  Everybody
+  // else meets the initialised barriers at the __syncthreads() below, before the first wait.
+  if ((tid & 31) == 0 && (tid >> 5) < NST) {
+    if (tid == 0) {
+      tma_prefetch_desc(&p.map_k);
+      tma_prefetch_desc(&p.map_v);
+    }
+    mbar_init(&full_bar[tid >> 5], 1);
     fence_mbar_init();
   }
-  if (tid == 32) {  // start fetching the K/V tensor maps before the first TMA needs them
-    tma_prefetch_desc(&p.map_k);
-    tma_prefetch_desc(&p.map_v);
-  }
-  __syncthreads();
 
   const __nv_bfloat16 *kb, *vb;
   int tb, te;
@@ -172,13 +174,14 @@ __global__ void __launch_bounds__(256, 1) attn_decode_mma_kernel(const __grid_co
   // so this happens before the dependency wait)
   if (is_prefix) {
     for (int s = 0; s < NST; ++s) {
-      if (s < n_tiles) load_tile(s, (s & 7) * 32);  // one warp per stage issues: the TMA ops of different
-      cp_async_commit();                             // stages enter the queue side by side, not one after another
+      if (s < n_tiles) load_tile(s, s * 32);  // the stage's own thread issues: the TMA ops of different stages
+      cp_async_commit();                       // enter the queue side by side, not one after another
     }
     phase_mark(1);
     pdl_wait();
     phase_mark(2);
   }
+  __syncthreads();  // barrier initialisation (and the suffix item's appended row) visible to the whole CTA
 
   // ---- stage the rotated, bf16-rounded query rows (rows past n_rows are zero): one thread handles
   // 8 consecutive rotation pairs of one row with 16-byte loads and stores
