@@ -626,6 +626,7 @@ struct advspec_engine {
   // decode graph cache
   cudaGraphExec_t graph = nullptr;
   std::vector<int> graph_key;
+  int64_t graph_launches = 0;  // kernels (and NCCL calls) one replay of `graph` launches
 
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -979,7 +980,7 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
                            (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o, e->dattn,
                            e->n_slots, d.head_dim));
       ADV_TRACE(e->stream, "attn_combine2");
-      e->launches -= 1;  // two kernels instead of rope + attention + combine (counted as 3 below)
+      e->launches += 2;  // attention (RoPE + append + split-KV) and the combine
     } else {
     E_CUDA(e, launch_pdl(rope_decode_kernel, dim3(b), dim3(256), 0, e->stream, true,
                            (const __nv_bfloat16*)e->dqkv, e->dq, suffix_k(e, l), suffix_v(e, l),
@@ -1010,6 +1011,7 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
                            (const float*)e->part_m, (const float*)e->part_l, (const float*)e->part_o,
                            e->dattn, e->n_slots, d.head_dim));
       ADV_TRACE(e->stream, "attn_combine");
+      e->launches += 3;  // rope, attention, combine
     }
     GemvParams g2{w.wo, e->dattn, nullptr, nullptr, e->dx, dm, HD, 0, tp_resadd_epi(e), d.act, d.norm_eps};
     E_CUDA(e, gemv(g2));
@@ -1022,7 +1024,6 @@ advspec_status enqueue_forward(advspec_engine* e, int b, float* gemv_ms_out) {
     E_CUDA(e, gemv(g4));
     if (advspec_status ts = tp_allreduce(e, e->dx, (size_t)b * dm)) return ts;
     ADV_TRACE(e->stream, "gemv down");
-    e->launches += 3;
   }
   GemvParams gl{lm_head_w(e), e->dx, final_norm_w(e), nullptr, e->dlogits, d.vocab_size, dm, 1, EPI_F32,
                 d.act, d.norm_eps};
@@ -1745,7 +1746,6 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
     key.push_back(e->prefix_gen);
     { int tbits; memcpy(&tbits, &temperature, sizeof tbits); key.push_back(tbits); }
     key.push_back(eos_id);
-    const int64_t per_step = (e->attn_fused ? 6 : 7) * (int64_t)d.n_layers + 3;
     if (e->use_graph) {
       if (!e->graph || e->graph_key != key) {
         if (e->graph) {
@@ -1758,7 +1758,8 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
         advspec_status fs = enqueue_forward(e, n, nullptr);
         cudaError_t le = launch_sampler(e, sp, n, true);
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
-        e->launches = before;  // capture only records; launches are counted per replay
+        e->graph_launches = e->launches - before;  // what one replay launches (counted while recording)
+        e->launches = before;                      // capture only records; launches are counted per replay
         if (fs != ADVSPEC_OK || le != cudaSuccess || ce != cudaSuccess) {
           if (g) cudaGraphDestroy(g);
           if (fs == ADVSPEC_OK)
@@ -1778,7 +1779,7 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
     for (int s = 0; s < steps; ++s) {
       if (e->use_graph) {
         E_CUDA(e, cudaGraphLaunch(e->graph, e->stream));
-        e->launches += per_step;
+        e->launches += e->graph_launches;
       } else {
         advspec_status fs = enqueue_forward(e, n, nullptr);
         if (fs != ADVSPEC_OK) return fs;
