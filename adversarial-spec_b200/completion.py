@@ -6,7 +6,9 @@ Only the fields the reference reads exist on the response:
 (models.py:629, 639-640).  The reference enters this function from N threads at
 once with identical ``messages`` when opponents share a model (models.py:699);
 those calls are coalesced here — the first caller waits until arrivals go quiet (5 ms
-without a new sibling, 25 ms at most), then ONE prefill serves them all.  Callers that can see the whole
+without a new sibling, 25 ms at most), then ONE prefill serves them all.  Concurrent calls for the same
+model and system prompt whose user messages differ join the same round: the engine shares whatever token
+prefix they have in common (``runtime.generate_group``).  Callers that can see the whole
 panel should use ``models.call_models_parallel`` (seam B2) instead.
 """
 
@@ -62,6 +64,7 @@ def _split_messages(messages: list[dict]) -> tuple[str, str]:
 class _Batch:
     def __init__(self):
         self.n = 0
+        self.users: list[str] = []
         self.closed = False
         self.results: Optional[list] = None
         self.done = threading.Event()
@@ -118,7 +121,7 @@ def completion(*, model: str, messages: list[dict], max_tokens: int = 8000, time
 
     spec = resolve(model)
     system, user = _split_messages(messages)
-    digest = hashlib.sha256((system + "\x00" + user).encode()).hexdigest()
+    digest = hashlib.sha256(system.encode()).hexdigest()
     key = (spec.name, digest, max_tokens, float(temperature))
     with _pending_mu:
         b = _pending.get(key)
@@ -128,6 +131,7 @@ def completion(*, model: str, messages: list[dict], max_tokens: int = 8000, time
             _pending[key] = b
         my = b.n
         b.n += 1
+        b.users.append(user)
         base = _call_counter
         _call_counter += 1
     if not leader:
@@ -140,9 +144,11 @@ def completion(*, model: str, messages: list[dict], max_tokens: int = 8000, time
             if _pending.get(key) is b:
                 del _pending[key]
             n = b.n
+            users = list(b.users)
         seeds = [runtime.opponent_seed(0, base * 16 + i) for i in range(n)]
         try:
-            b.results = runtime.run_round([model] * n, system, user, seeds, max_tokens, temperature)
+            b.results = runtime.run_round([model] * n, system, user if len(set(users)) == 1 else users, seeds,
+                                          max_tokens, temperature)
         except Exception as ex:
             b.results = [ex] * n
         b.done.set()

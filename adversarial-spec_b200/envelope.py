@@ -14,7 +14,7 @@ from __future__ import annotations
 import importlib.util
 import os
 from pathlib import Path
-from typing import Optional
+from typing import Optional, Sequence
 
 SYSTEM_PROMPT_PRD = """You are a senior product manager taking part in adversarial spec development: several reviewers challenge a Product Requirements Document until it is ready to hand to engineering.
 
@@ -179,3 +179,32 @@ def build_messages(spec: str, round_num: int, doc_type: str, press: bool = False
     user_message = template.format(round=round_num, doc_type_name=get_doc_type_name(doc_type), spec=spec,
                                    focus_section=focus_section, context_section=context if context else "")
     return system_prompt, user_message
+
+
+PERSONA_TAIL_HEADER = "For this review, answer from the following perspective.\n"
+
+
+def persona_tail(doc_type: str, persona: str) -> str:
+    """What a per-opponent persona adds at the END of the user message: the persona's own prompt text
+    (`get_system_prompt(doc_type, persona)`, prompts.py:290-304) under a one-line header."""
+    return "\n\n" + PERSONA_TAIL_HEADER + get_system_prompt(doc_type, persona)
+
+
+def build_panel_messages(spec: str, round_num: int, doc_type: str, press: bool, focus: Optional[str],
+                         personas: Sequence[Optional[str]], context: Optional[str] = None,
+                         preserve_intent: bool = False) -> tuple[str, list[str]]:
+    """(system_prompt, one user message per opponent) for a panel whose opponents may each have a persona of
+    their own (SURVEY.md §8(f4) — not in the reference, where `--persona` is one flag for the whole panel,
+    debate.py:835, and replaces the SYSTEM prompt, i.e. the first tokens of the prompt).
+
+    One persona for everyone (or none): exactly `build_messages`, the reference's layout.  Different personas:
+    the variable text moves BEHIND the document — the system prompt is the doc type's default for every
+    opponent and each persona's text closes that opponent's user message — so the prompts share every token up
+    to the end of the review instruction and the engine prefills that prefix once for the whole panel."""
+    personas = list(personas)
+    if len(set(personas)) <= 1:
+        system_prompt, user = build_messages(spec, round_num, doc_type, press, focus,
+                                             personas[0] if personas else None, context, preserve_intent)
+        return system_prompt, [user] * len(personas)
+    system_prompt, user = build_messages(spec, round_num, doc_type, press, focus, None, context, preserve_intent)
+    return system_prompt, [user + (persona_tail(doc_type, p) if p else "") for p in personas]

@@ -119,9 +119,21 @@ def is_local_model(model: str) -> bool:
     return model.startswith(LOCAL_PREFIXES)
 
 
+def split_persona(model: str) -> tuple[str, Optional[str]]:
+    """``b200/<name>@<persona>`` -> (``b200/<name>``, persona): a per-opponent persona (the
+    reference has one global ``--persona`` for the whole panel, debate.py:835).  Only local model strings carry
+    the suffix — remote provider ids may contain ``@`` themselves and pass through untouched."""
+    if is_local_model(model) and "@" in model:
+        base, persona = model.split("@", 1)
+        return base, (persona.strip() or None)
+    return model, None
+
+
 def resolve(model: str) -> ModelSpec:
-    """``b200/<name>`` or ``local/<name>`` (or a bare registry name) -> ModelSpec."""
-    key = model
+    """``b200/<name>`` or ``local/<name>`` (or a bare registry name), with or without an ``@persona`` suffix
+    -> ModelSpec."""
+    key = split_persona(model)[0]
+    model = key
     for p in LOCAL_PREFIXES:
         if model.startswith(p):
             key = model[len(p):]

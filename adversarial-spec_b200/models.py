@@ -26,8 +26,8 @@ from typing import Optional
 
 from . import runtime
 from .completion import completion  # seam B1; tests patch ``models.completion`` like the reference's
-from .envelope import build_messages
-from .model_spec import is_local_model
+from .envelope import build_messages, build_panel_messages
+from .model_spec import is_local_model, split_persona
 from .providers import DEFAULT_CODEX_REASONING, DEFAULT_COST, MODEL_COSTS
 
 MAX_RETRIES = 3
@@ -59,7 +59,7 @@ class CostTracker:
     by_model: dict = field(default_factory=dict)
 
     def add(self, model: str, input_tokens: int, output_tokens: int) -> float:
-        rate = MODEL_COSTS.get(model, DEFAULT_COST)
+        rate = MODEL_COSTS.get(model) or MODEL_COSTS.get(split_persona(model)[0], DEFAULT_COST)
         cost = input_tokens / 1_000_000 * rate["input"] + output_tokens / 1_000_000 * rate["output"]
         self.total_input_tokens += input_tokens
         self.total_output_tokens += output_tokens
@@ -223,15 +223,20 @@ def _call_local_panel(local: list[tuple[int, str]], spec: str, round_num: int, d
     raises (or whose name is unknown) are retried together on the reference's schedule — one back-off per
     attempt, as the reference's threads sleep in parallel — then reported per opponent.  `timeout` bounds
     each attempt like the per-call timeout of the reference (models.py:621)."""
-    system_prompt, user_message = build_messages(spec, round_num, doc_type, press, focus, persona, context,
-                                                 preserve_intent)
     names = [m for _, m in local]
+    # `b200/<model>@<persona>` gives that opponent a persona of its own (SURVEY.md §8(f4)); the others keep
+    # the panel's --persona.  With one persona for everyone this is exactly build_messages.
+    personas = [split_persona(m)[1] or persona for m in names]
+    system_prompt, user_messages = build_panel_messages(spec, round_num, doc_type, press, focus, personas,
+                                                        context, preserve_intent)
+    same = len(set(user_messages)) <= 1
     seeds = [runtime.opponent_seed(round_num, i) for i, _ in local]
     done: dict[int, ModelResponse] = {}
     pending = list(range(len(local)))
     for attempt in range(MAX_RETRIES):
         one = concurrent.futures.ThreadPoolExecutor(max_workers=1)
-        fut = one.submit(runtime.run_round, [names[j] for j in pending], system_prompt, user_message,
+        fut = one.submit(runtime.run_round, [names[j] for j in pending], system_prompt,
+                         user_messages[0] if same else [user_messages[j] for j in pending],
                          [seeds[j] for j in pending], 8000, 0.7)
         try:
             outs = fut.result(timeout=timeout if timeout and timeout > 0 else None)

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import os
 import threading
+import time
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
@@ -119,6 +120,7 @@ class Generation:
     token_ids: list[int]
     prefill_ms: float = 0.0
     decode_ms: float = 0.0
+    tail_ms: float = 0.0  # per-opponent prompt tails stepped through the decode path (per-opponent personas)
 
 
 class HFTokenizerAdapter:
@@ -357,25 +359,96 @@ def opponent_seed(round_num: int, index: int) -> int:
     return (base * 1_000_003 + round_num * 1009 + index * 7919 + 1) & ((1 << 63) - 1)
 
 
-def generate_group(spec: ModelSpec, device: int, system_prompt: str, user_message: str, n_opponents: int,
+def _common_prefix_len(seqs: Sequence[Sequence[int]]) -> int:
+    n = min(len(q) for q in seqs)
+    first = np.asarray(seqs[0][:n], dtype=np.int64)
+    for q in seqs[1:]:
+        neq = np.nonzero(np.asarray(q[:n], dtype=np.int64) != first[:n])[0]
+        if neq.size:
+            n = int(neq[0])
+    return n
+
+
+def plan_tails(prompts: Sequence[Sequence[int]], tail_max: int, min_frac: float = 0.5):
+    """Split the prompts of one batch into (tokens of the shared prefix, one tail per opponent), or None
+    when they should not share: nothing in common, a tail longer than `tail_max`, or a shared part shorter
+    than `min_frac` of the shortest prompt.  Every tail keeps at least one token — the step that consumes an
+    opponent's last prompt token is the one that produces its first next-token logits."""
+    keep = min(_common_prefix_len(prompts), min(len(q) for q in prompts) - 1)
+    if keep < 1 or keep < min_frac * min(len(q) for q in prompts):
+        return None
+    tails = [list(q[keep:]) for q in prompts]
+    if max(len(t) for t in tails) > tail_max:
+        return None
+    return list(prompts[0][:keep]), tails
+
+
+def step_tails(e, seq_ids: Sequence[int], tails: Sequence[Sequence[int]]) -> int:
+    """Feed each opponent the tokens its prompt has beyond the shared prefix, teacher-forced through the
+    batched decode step (`advspec_decode_step`): the tails are RIGHT-aligned, so the opponents with the
+    longest tails start alone and the final step carries every opponent in fork order — which is what
+    `advspec_decode` needs to sample each opponent's first token from that step's logits.  Returns the
+    number of steps."""
+    longest = max(len(t) for t in tails)
+    for t in range(longest):
+        part = [(sid, tl[t - (longest - len(tl))]) for sid, tl in zip(seq_ids, tails) if t >= longest - len(tl)]
+        e.decode_step([sid for sid, _ in part], [f for _, f in part])
+    return longest
+
+
+def generate_group(spec: ModelSpec, device: int, system_prompt: str, user_message, n_opponents: int,
                    seeds: Sequence[int], max_tokens: int, temperature: float) -> list[Generation]:
-    """One shared-prefix round for `n_opponents` opponents of one model on one GPU."""
+    """One round for `n_opponents` opponents of one model on one GPU.  `user_message` is one string for the
+    whole panel (the reference's case: identical messages, one shared-prefix prefill) or one string per
+    opponent (per-opponent personas): opponents whose prompts differ only at the end still
+    share ONE prefill of the common tokens and decode as ONE batch; each opponent's own tail is stepped
+    through the decode path first (`step_tails`).  Prompts that differ early (or by more than
+    ADVSPEC_TAIL_MAX tokens, default 512) fall back to one prefill + decode per distinct prompt."""
     tok, _ = tokenizer_for(spec)
-    prompt_ids = tok.encode(render_prompt(tok, system_prompt, user_message), bos=True)
+    users = [user_message] * n_opponents if isinstance(user_message, str) else list(user_message)
+    if len(users) != n_opponents:
+        raise ValueError(f"{len(users)} user messages for {n_opponents} opponents")
+    encoded: dict[str, list[int]] = {}
+    for u in users:
+        if u not in encoded:
+            encoded[u] = tok.encode(render_prompt(tok, system_prompt, u), bos=True)
+    prompts = [encoded[u] for u in users]
     max_new = effective_max_new(max_tokens)
-    out: list[Generation] = []
-    with POOL.lease(spec, device, len(prompt_ids), max_new) as res, res.lock:
+    tail_max = _env_int("ADVSPEC_TAIL_MAX", 512)
+    # batches of at most MAX_BATCH opponents, each: (indices, shared prefix tokens, tails or None)
+    work: list[tuple[list[int], list[int], Optional[list[list[int]]]]] = []
+    for g0 in range(0, n_opponents, MAX_BATCH):
+        idx = list(range(g0, min(n_opponents, g0 + MAX_BATCH)))
+        mine = [prompts[i] for i in idx]
+        if all(q is mine[0] or q == mine[0] for q in mine):
+            work.append((idx, mine[0], None))
+            continue
+        plan = plan_tails(mine, tail_max)
+        if plan is not None:
+            work.append((idx, plan[0], plan[1]))
+            continue
+        by_prompt: dict[str, list[int]] = {}
+        for i in idx:
+            by_prompt.setdefault(users[i], []).append(i)
+        work.extend((ii, prompts[ii[0]], None) for ii in by_prompt.values())
+    longest_tail = max([len(t) for _, _, tails in work if tails for t in tails] or [0])
+    out: list[Optional[Generation]] = [None] * n_opponents
+    with POOL.lease(spec, device, max(len(q) for q in prompts), max_new + longest_tail) as res, res.lock:
         e = res.engine
-        for g0 in range(0, n_opponents, MAX_BATCH):
-            batch_seeds = list(seeds[g0: g0 + MAX_BATCH])
-            pid = PREFIXES.prefill(e, (spec.name, device), prompt_ids)
-            ids = e.fork(pid, batch_seeds)
+        for idx, prefix_ids, tails in work:
+            pid = PREFIXES.prefill(e, (spec.name, device), prefix_ids)
+            ids = e.fork(pid, [seeds[i] for i in idx])
+            tail_ms = 0.0
+            if tails is not None:
+                t0 = time.perf_counter()
+                step_tails(e, ids, tails)
+                tail_ms = (time.perf_counter() - t0) * 1e3
             dec = e.decode(ids, max_new, temperature=temperature, eos_id=tok.eos_id)
             tm = e.timing()
-            for toks in dec.tokens:
+            for i, toks in zip(idx, dec.tokens):
                 body = toks[:-1] if (toks and toks[-1] == tok.eos_id) else toks
-                out.append(Generation(res.tok.decode(body), len(prompt_ids), len(toks), toks,
-                                      tm.prefill_ms, tm.decode_ms))
+                out[i] = Generation(res.tok.decode(body), len(prompts[i]), len(toks), toks,
+                                    tm.prefill_ms, tm.decode_ms, tail_ms)
             e.release_seqs(ids)
     return out
 
@@ -417,10 +490,13 @@ def plan_placement(model_names: Sequence[str], devices: Sequence[int], policy: O
     return list(merged.values())
 
 
-def run_round(model_names: Sequence[str], system_prompt: str, user_message: str, seeds: Sequence[int],
+def run_round(model_names: Sequence[str], system_prompt: str, user_message, seeds: Sequence[int],
               max_tokens: int, temperature: float, devices: Optional[Sequence[int]] = None) -> list:
-    """All local opponents of one critique round.  Returns, per opponent (input order), a
-    Generation or the Exception its group raised."""
+    """All local opponents of one critique round.  `user_message`: one string for the panel, or one per
+    opponent (per-opponent personas).  Returns, per opponent (input order), a Generation or the Exception
+    its group raised."""
+    if not isinstance(user_message, str) and len(user_message) != len(model_names):
+        raise ValueError(f"{len(user_message)} user messages for {len(model_names)} opponents")
     devices = list(devices) if devices is not None else visible_devices()
     results: list = [None] * len(model_names)
     known: list[int] = []
@@ -436,7 +512,8 @@ def run_round(model_names: Sequence[str], system_prompt: str, user_message: str,
 
     def work(p: Placement):
         try:
-            gens = generate_group(p.spec, p.device, system_prompt, user_message, len(p.indices),
+            users = user_message if isinstance(user_message, str) else [user_message[i] for i in p.indices]
+            gens = generate_group(p.spec, p.device, system_prompt, users, len(p.indices),
                                   [seeds[i] for i in p.indices], max_tokens, temperature)
             for i, g in zip(p.indices, gens):
                 results[i] = g

@@ -31,6 +31,8 @@ GPUs of this run:
            adds the one-opponent-per-GPU placement
   tp       config 5 (N >= 2): one Llama-3-70B opponent tensor-parallel over the N GPUs,
            32K-token spec: decode HBM fraction per GPU, prefill TF/s per GPU
+  personas SURVEY.md §8(f4): the headline panel with a different persona per opponent
+           (`b200/llama-3-8b@<persona>`) against one persona for everyone, per rank
 Each section is optional (`--sections`) and guarded: a failure or a time-out there is
 reported in its own key and never costs the headline.
 
@@ -56,7 +58,7 @@ if str(ROOT) not in sys.path:
 _emit = lambda line: print(json.dumps(line), flush=True)
 METRIC = "aggregate_critique_tokens_per_sec"
 UNIT = "tokens/s"
-ALL_SECTIONS = ("strong", "hetero", "converge", "tp")
+ALL_SECTIONS = ("strong", "personas", "hetero", "converge", "tp")
 HETERO_PANEL = ["llama-3-8b", "mistral-7b", "qwen2-7b", "phi-3-mini", "gemma-7b"]
 
 
@@ -78,7 +80,7 @@ def parse_args():
                     help="reference arm: wall-time budget for all (warmup + steps) samples")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sections", default="all",
-                    help="comma list of extra sections (strong,hetero,converge,tp), 'all' or 'none'")
+                    help="comma list of extra sections (strong,personas,hetero,converge,tp), 'all' or 'none'")
     ap.add_argument("--sections-budget-s", type=float, default=420.0)
     ap.add_argument("--traffic", default="auto", choices=["auto", "off"],
                     help="auto: measure the GEMV's DRAM traffic with an ncu pass (N=1, when ncu is on PATH)")
@@ -431,6 +433,46 @@ def section_strong(args, D, peaks):
             "s_per_round": wall / 2, "per_rank": rows}
 
 
+def section_personas(args, D, peaks):
+    """the headline panel (3 x Llama-3-8B, 4,096-token PRD) with a persona per opponent
+    (`b200/llama-3-8b@<persona>`: persona text behind the document, ONE prefill of the shared tokens, the
+    per-opponent tails stepped through the batched decode path, one decode batch) beside the reference's
+    layout (one `--persona` for the whole panel, in the system prompt).  Every rank runs its own panel."""
+    from advspec_b200 import models as amodels, model_spec, runtime
+
+    spec = model_spec.resolve("llama-3-8b")
+    doc = make_doc(spec.vocab_size, 4096, 2024, "Synthetic PRD")
+    os.environ["ADVSPEC_SEED"] = str(3000 + D.rank)
+    people = ("security-engineer", "oncall-engineer", "junior-developer")
+    cases = (("one_persona_for_the_panel", ["b200/llama-3-8b"] * 3, people[0]),
+             ("persona_per_opponent", [f"b200/llama-3-8b@{p}" for p in people], None))
+    row = {"rank": D.rank}
+    for label, panel, persona in cases:
+        wall, res, before = 0.0, [], {}
+        for rep in range(2):  # the first round may re-create the engine (larger suffix KV) and captures the graph
+            before = dict(runtime.PREFIXES.stats)
+            D.barrier()
+            t0 = time.perf_counter()
+            res = amodels.call_models_parallel(panel, doc, 70 + rep, "prd", False, None, persona)
+            wall = time.perf_counter() - t0
+        st = engine_stats(spec, D.local_rank, peaks)
+        after = runtime.PREFIXES.stats
+        prefilled = after["tokens_prefilled"] - before.get("tokens_prefilled", 0)
+        toks = sum(r.output_tokens for r in res)
+        row[label] = {"wall_s": wall, "tokens": toks, "tokens_per_s": toks / wall if wall > 0 else None,
+                      "input_tokens": sorted(r.input_tokens for r in res), "tokens_prefilled": prefilled,
+                      "tail_steps": max(r.input_tokens for r in res) - prefilled if res else None,
+                      "prefills": after["full"] - before.get("full", 0), "errors": [r.error for r in res if r.error],
+                      **st}
+    rows = D.gather(row)
+    out = {"workload": "3 x Llama-3-8B, 4,096-token PRD, %d new tokens each; persona per opponent vs one for the "
+                       "panel; one panel per rank" % args.gen, "per_rank": rows}
+    for label, _, _ in cases:
+        wall = max(r[label]["wall_s"] for r in rows)
+        out[label + "_tokens_per_s"] = sum(r[label]["tokens"] for r in rows) / wall if wall > 0 else None
+    return out
+
+
 def section_hetero(args, D, peaks):
     """Config 3: Llama-3-8B / Mistral-7B / Qwen2-7B / Phi-3-mini / Gemma-7B, 8,192-token tech spec, models
     round-robin over the N GPUs (N >= 5: one model per GPU), each with its own prefill, no collective.  A
@@ -593,7 +635,7 @@ def section_tp(args, D, peaks):
                 os.environ[k] = v
 
 
-SECTION_FNS = {"strong": section_strong, "hetero": section_hetero, "converge": section_converge, "tp": section_tp}
+SECTION_FNS = {"strong": section_strong, "personas": section_personas, "hetero": section_hetero, "converge": section_converge, "tp": section_tp}
 
 
 # ----------------------------------------------------------------------------- DRAM traffic (ncu pass)

@@ -162,6 +162,60 @@ def test_prefix_reuse_across_calls_matches_a_full_prefill(cuda_device, diag, mon
     assert r2[0].input_tokens > r1[0].input_tokens
 
 
+def test_per_opponent_tails_match_hf_and_share_one_prefill(cuda_device, diag, monkeypatch):
+    """opponents whose prompts differ only at the end (per-opponent personas) share ONE
+    prefill of the common tokens; each opponent's own tail is teacher-forced through the batched decode step,
+    right-aligned, with tails of different lengths (37 / 1 / 12 tokens: the batch is 1, then 2, then 3
+    opponents wide and every opponent sits at a different position).  The logits each opponent samples its
+    first token from must match an HF forward of ITS full prompt, and greedy decoding must continue from
+    them within the stated tolerance."""
+    from oracle import hf_oracle
+    from tests.gpu_util import TOL_MAX, TOL_RMS, make_engine, rel_errors
+    import numpy as np
+
+    spec, model, e = make_engine("tiny-llama-128", 41, max_prefix=2048, max_new=128)
+    rng = np.random.default_rng(8)
+    head = rng.integers(0, spec.vocab_size, 700).tolist()
+    tails_in = [rng.integers(0, spec.vocab_size, n).tolist() for n in (37, 1, 12)]
+    prompts = [head + t for t in tails_in]
+    shared, tails = runtime.plan_tails(prompts, tail_max=64)
+    assert shared == head and tails == tails_in
+    pid = e.prefill(shared)
+    ids = e.fork(pid, [1, 2, 3])
+    assert runtime.step_tails(e, ids, tails) == 37
+    lg = e.get_logits(3)
+    worst = (0.0, 0.0)
+    for i in range(3):
+        mx, rms = rel_errors(lg[i], hf_oracle.hf_logits(model, prompts[i])[-1])
+        worst = (max(worst[0], mx), max(worst[1], rms))
+    diag["persona_tails/tiny-llama-128"] = {"max": worst[0], "rms": worst[1]}
+    assert worst[0] < TOL_MAX and worst[1] < TOL_RMS, worst
+    res = e.decode(ids, 6, temperature=0.0)
+    assert res.lens == [6, 6, 6]
+    for i in range(3):
+        assert res.tokens[i][0] == int(lg[i].argmax())  # token 0 comes from the last tail step's logits
+        hist = list(prompts[i])
+        for tok in res.tokens[i]:
+            ref = hf_oracle.hf_logits(model, hist)[-1]
+            assert ref.max() - ref[tok] <= TOL_MAX * ref.std(), (i, tok, int(ref.argmax()))
+            hist.append(tok)
+    e.close()
+
+    # through seam B2: three personas, one prefill, one decode batch of three
+    monkeypatch.setattr(models.time, "sleep", lambda s: None)
+    monkeypatch.setattr(models, "cost_tracker", models.CostTracker())
+    runtime.PREFIXES.stats.update(full=0, extended=0, rearmed=0, tokens_reused=0, tokens_prefilled=0)
+    panel = ["b200/tiny-llama@security-engineer", "b200/tiny-llama@oncall-engineer", "b200/tiny-llama"]
+    res = models.call_models_parallel(panel, _spec(1200), 1, "prd")
+    assert sorted(r.model for r in res) == sorted(panel) and all(r.error is None and r.output_tokens == 12 for r in res)
+    by = {r.model: r for r in res}
+    assert by[panel[0]].input_tokens > by[panel[2]].input_tokens and by[panel[1]].input_tokens > by[panel[2]].input_tokens
+    st = runtime.PREFIXES.stats
+    assert (st["full"], st["extended"]) == (1, 0) and st["tokens_prefilled"] < by[panel[2]].input_tokens
+    eng = next(iter(runtime.POOL._engines.values())).engine
+    assert eng.timing().decode_batch == 3, "three personas, ONE decode batch"
+
+
 def test_resident_server_keeps_engines_across_cli_invocations(cuda_device, tmp_path):
     """the reference runs one `debate.py` process per round (`--session`, then
     `--resume`); with the resident server the second and third invocation find the engine loaded."""
