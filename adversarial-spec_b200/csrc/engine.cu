@@ -550,6 +550,21 @@ __global__ void advance_kernel(const int* slots, int* suf_len) {
   suf_len[slots[threadIdx.x]] += 1;
 }
 
+// advspec_append_tail: K/V rows [row0, row0 + n) of every (layer, K|V, KV head) of the prefix region
+// ([L][2][Hkv][pstride][dh]) -> rows [0, n) of opponent `slot` in the suffix region ([L][2][slot][Hkv][sstride][dh]).
+// grid (L * 2, Hkv); 16-byte vectors (dh * 2 bytes is a multiple of 16 for every head_dim served).
+__global__ void kv_tail_to_suffix_kernel(const __nv_bfloat16* __restrict__ pkv, __nv_bfloat16* __restrict__ skv,
+                                         size_t pkv_layer_elems, size_t skv_layer_elems, int Hkv, int64_t pstride,
+                                         int64_t sstride, int dh, int slot, int row0, int n) {
+  const int lk = blockIdx.x, hk = blockIdx.y;  // lk = layer * 2 + (0: K, 1: V)
+  const uint4* src = reinterpret_cast<const uint4*>(pkv + (size_t)lk * pkv_layer_elems +
+                                                    ((size_t)hk * pstride + row0) * dh);
+  uint4* dst = reinterpret_cast<uint4*>(skv + (size_t)lk * skv_layer_elems +
+                                        ((size_t)slot * Hkv + hk) * sstride * dh);
+  const int vecs = n * dh / 8;
+  for (int i = threadIdx.x; i < vecs; i += blockDim.x) dst[i] = src[i];
+}
+
 }  // namespace
 
 // ============================================================================
@@ -621,6 +636,7 @@ struct advspec_engine {
   bool slot_used[8] = {false, false, false, false, false, false, false, false};
   std::vector<int> h_suf_len = std::vector<int>(8, 0);
   bool logits_broadcast = true;  // current logits are the prefill's (shared) ones
+  bool tails_open = false;       // advspec_append_tail is filling dlogits rows in logits_slots order
   std::vector<int> logits_slots;  // batch order of dlogits when !logits_broadcast
 
   // decode graph cache
@@ -1617,6 +1633,7 @@ advspec_status advspec_prefill(advspec_engine* e, const int32_t* tokens, int32_t
   e->prefix_gen = next_gen++;
   e->prefix_len = n_tokens;
   e->logits_broadcast = true;
+  e->tails_open = false;
   *prefix_id = e->prefix_gen;
   return ADVSPEC_OK;
 }
@@ -1649,6 +1666,7 @@ advspec_status advspec_prefill_extend(advspec_engine* e, int32_t prefix_id, int3
   e->prefix_gen = next_gen++;
   e->prefix_len = keep_tokens + n_tokens;
   e->logits_broadcast = true;
+  e->tails_open = false;
   *new_prefix_id = e->prefix_gen;
   return ADVSPEC_OK;
 }
@@ -1724,7 +1742,7 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
     return ADVSPEC_ERR_INVALID;
   }
   if (!e->logits_broadcast && e->logits_slots != slots) {
-    e->fail("decode after decode_step must use the same opponents in the same order");
+    e->fail("decode after decode_step / append_tail must use the same opponents in the same order");
     return ADVSPEC_ERR_STATE;
   }
   const int zero = 0;
@@ -1821,7 +1839,64 @@ advspec_status advspec_decode(advspec_engine* e, const int32_t* seq_ids, int32_t
   }
   e->logits_broadcast = false;
   e->logits_slots = slots;
+  e->tails_open = false;
   return ADVSPEC_OK;
+}
+
+advspec_status advspec_append_tail(advspec_engine* e, int32_t seq_id, const int32_t* tokens, int32_t n_tokens) {
+  if (!e || !tokens) return ADVSPEC_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  const auto& d = e->d;
+  if (e->prefix_gen == 0) {
+    e->fail("append_tail: no live prefix");
+    return ADVSPEC_ERR_STATE;
+  }
+  if (seq_id < 0 || seq_id >= d.max_seqs || !e->slot_used[seq_id]) {
+    e->fail("append_tail: opponent %d is not forked", seq_id);
+    return ADVSPEC_ERR_INVALID;
+  }
+  if (e->h_suf_len[seq_id] != 0) {
+    e->fail("append_tail: opponent %d already holds %d tokens of its own; a tail directly follows the fork", seq_id,
+            e->h_suf_len[seq_id]);
+    return ADVSPEC_ERR_STATE;
+  }
+  if (n_tokens < 1 || n_tokens > d.max_new_tokens) {
+    e->fail("append_tail: %d tokens outside 1..%d (suffix KV capacity)", n_tokens, d.max_new_tokens);
+    return ADVSPEC_ERR_INVALID;
+  }
+  if (!e->tails_open) e->logits_slots.clear();
+  if ((int)e->logits_slots.size() >= d.max_seqs) {
+    e->fail("append_tail: more tails than opponents");
+    return ADVSPEC_ERR_STATE;
+  }
+  // The tail runs as a prompt chunk at positions prefix_len.. against the prefix KV; its own K/V lands in the
+  // prefix region's rows PAST the live prefix (scratch until the next tail or extension), the prefix and its
+  // forks stay as they are.
+  const int gen = e->prefix_gen;
+  bool used[8];
+  std::copy(std::begin(e->slot_used), std::end(e->slot_used), used);
+  const float prefix_ms = e->tm.prefill_ms;
+  advspec_status st = prefill_impl(e, tokens, n_tokens, nullptr, e->prefix_len);
+  e->prefix_gen = gen;
+  std::copy(used, used + 8, std::begin(e->slot_used));
+  if (st != ADVSPEC_OK) return st;
+  e->tm.prefill_ms += prefix_ms;  // prompt processing of the round: shared prefix + tails
+  kv_tail_to_suffix_kernel<<<dim3(d.n_layers * 2, d.n_kv_heads), 256, 0, e->stream>>>(
+      e->pkv, e->skv, e->pkv_layer_elems, e->skv_layer_elems, d.n_kv_heads, (int64_t)d.max_prefix_tokens,
+      (int64_t)d.max_new_tokens, d.head_dim, seq_id, e->prefix_len, n_tokens);
+  E_CUDA(e, cudaGetLastError());
+  e->launches++;
+  const int row = (int)e->logits_slots.size();
+  E_CUDA(e, cudaMemcpyAsync(e->dlogits + (size_t)row * d.vocab_size, e->prefill_logits,
+                            (size_t)d.vocab_size * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+  e->h_suf_len[seq_id] = n_tokens;
+  E_CUDA(e, cudaMemcpyAsync(e->s_suf_len + seq_id, &e->h_suf_len[seq_id], sizeof(int), cudaMemcpyHostToDevice,
+                            e->stream));
+  E_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->logits_slots.push_back(seq_id);
+  e->logits_broadcast = false;
+  e->tails_open = true;
+  return check_watchdog(e);
 }
 
 advspec_status advspec_decode_step(advspec_engine* e, const int32_t* seq_ids, int32_t n,
@@ -1855,6 +1930,7 @@ advspec_status advspec_decode_step(advspec_engine* e, const int32_t* seq_ids, in
   for (int s : slots) e->h_suf_len[s] += 1;
   e->logits_broadcast = false;
   e->logits_slots = slots;
+  e->tails_open = false;
   return check_watchdog(e);
 }
 
@@ -1905,6 +1981,7 @@ advspec_status advspec_prefix_adopt(advspec_engine* e, int32_t n_tokens, const f
   e->prefix_gen = next_gen++;
   e->prefix_len = n_tokens;
   e->logits_broadcast = true;
+  e->tails_open = false;
   *prefix_id = e->prefix_gen;
   return ADVSPEC_OK;
 }

@@ -77,7 +77,7 @@ EXPORTED_SYMBOLS = [
     "advspec_tp_ipc_export", "advspec_tp_ipc_import",
     "advspec_load_weights",
     "advspec_init_weights_random", "advspec_set_rope_inv_freq", "advspec_prefill", "advspec_prefill_extend", "advspec_fork",
-    "advspec_decode", "advspec_decode_step", "advspec_get_logits", "advspec_prefill_logits",
+    "advspec_decode", "advspec_append_tail", "advspec_decode_step", "advspec_get_logits", "advspec_prefill_logits",
     "advspec_release_seqs", "advspec_release_prefix", "advspec_prefix_kv_region",
     "advspec_prefix_adopt", "advspec_get_timing", "advspec_profile_decode_step",
     "advspec_decode_step_bytes", "advspec_ktrace_enable", "advspec_ktrace_read", "advspec_ktrace_phases", "advspec_op_gemm", "advspec_op_gemm_check", "advspec_op_gemv",
@@ -116,6 +116,7 @@ def load_library() -> C.CDLL:
         "advspec_prefill_extend": (i32, [vp, i32, i32, P(i32), i32, P(i32)]),
         "advspec_fork": (i32, [vp, i32, i32, P(C.c_uint64), P(i32)]),
         "advspec_decode": (i32, [vp, P(i32), i32, i32, f32, i32, P(i32), P(i32)]),
+        "advspec_append_tail": (i32, [vp, i32, P(i32), i32]),
         "advspec_decode_step": (i32, [vp, P(i32), i32, P(i32)]),
         "advspec_get_logits": (i32, [vp, i32, P(f32)]),
         "advspec_prefill_logits": (i32, [vp, P(i32), i32, P(f32)]),
@@ -278,6 +279,11 @@ class Engine:
                                             C.c_float(temperature), eos_id, _p(out, C.c_int32),
                                             _p(lens, C.c_int32)))
         return DecodeResult([out[i, : lens[i]].tolist() for i in range(len(ids))], lens.tolist())
+
+    def append_tail(self, seq_id: int, tokens: Sequence[int]) -> None:
+        """Continue the shared prefix with `tokens` for ONE freshly forked opponent (per-opponent prompt tail)."""
+        t = _i32(tokens)
+        self._check(self.lib.advspec_append_tail(self.h, int(seq_id), _p(t, C.c_int32), t.size))
 
     def decode_step(self, seq_ids: Sequence[int], forced_tokens: Sequence[int]) -> None:
         ids, f = _i32(seq_ids), _i32(forced_tokens)

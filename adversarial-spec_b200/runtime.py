@@ -120,7 +120,7 @@ class Generation:
     token_ids: list[int]
     prefill_ms: float = 0.0
     decode_ms: float = 0.0
-    tail_ms: float = 0.0  # per-opponent prompt tails stepped through the decode path (per-opponent personas)
+    tail_ms: float = 0.0  # wall time of feeding the per-opponent prompt tails (per-opponent personas)
 
 
 class HFTokenizerAdapter:
@@ -396,14 +396,26 @@ def step_tails(e, seq_ids: Sequence[int], tails: Sequence[Sequence[int]]) -> int
     return longest
 
 
+def feed_tails(e, seq_ids: Sequence[int], tails: Sequence[Sequence[int]]) -> None:
+    """Give every freshly forked opponent the prompt tokens it has beyond the shared prefix.  Default: one
+    GEMM-shaped prompt chunk per opponent (`advspec_append_tail`: one pass over the weights per TAIL, its K/V
+    moved into the opponent's own KV).  ADVSPEC_TAIL_IMPL=step feeds the tails token by token through the
+    batched decode step instead (one pass over the weights per TOKEN of the longest tail; the A/B)."""
+    if os.environ.get("ADVSPEC_TAIL_IMPL", "chunk") == "step":
+        step_tails(e, seq_ids, tails)
+        return
+    for sid, tail in zip(seq_ids, tails):  # fork order = the decode batch's order
+        e.append_tail(sid, tail)
+
+
 def generate_group(spec: ModelSpec, device: int, system_prompt: str, user_message, n_opponents: int,
                    seeds: Sequence[int], max_tokens: int, temperature: float) -> list[Generation]:
     """One round for `n_opponents` opponents of one model on one GPU.  `user_message` is one string for the
     whole panel (the reference's case: identical messages, one shared-prefix prefill) or one string per
     opponent (per-opponent personas): opponents whose prompts differ only at the end still
-    share ONE prefill of the common tokens and decode as ONE batch; each opponent's own tail is stepped
-    through the decode path first (`step_tails`).  Prompts that differ early (or by more than
-    ADVSPEC_TAIL_MAX tokens, default 512) fall back to one prefill + decode per distinct prompt."""
+    share ONE prefill of the common tokens and decode as ONE batch; each opponent's own tail is fed after
+    the fork (`feed_tails`).  Prompts that differ early (or by more than ADVSPEC_TAIL_MAX tokens, default
+    512) fall back to one prefill + decode per distinct prompt."""
     tok, _ = tokenizer_for(spec)
     users = [user_message] * n_opponents if isinstance(user_message, str) else list(user_message)
     if len(users) != n_opponents:
@@ -441,7 +453,7 @@ def generate_group(spec: ModelSpec, device: int, system_prompt: str, user_messag
             tail_ms = 0.0
             if tails is not None:
                 t0 = time.perf_counter()
-                step_tails(e, ids, tails)
+                feed_tails(e, ids, tails)
                 tail_ms = (time.perf_counter() - t0) * 1e3
             dec = e.decode(ids, max_new, temperature=temperature, eos_id=tok.eos_id)
             tm = e.timing()

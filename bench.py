@@ -444,11 +444,14 @@ def section_personas(args, D, peaks):
     doc = make_doc(spec.vocab_size, 4096, 2024, "Synthetic PRD")
     os.environ["ADVSPEC_SEED"] = str(3000 + D.rank)
     people = ("security-engineer", "oncall-engineer", "junior-developer")
-    cases = (("one_persona_for_the_panel", ["b200/llama-3-8b"] * 3, people[0]),
-             ("persona_per_opponent", [f"b200/llama-3-8b@{p}" for p in people], None))
+    per = [f"b200/llama-3-8b@{p}" for p in people]
+    cases = (("one_persona_for_the_panel", ["b200/llama-3-8b"] * 3, people[0], None),
+             ("persona_per_opponent", per, None, "chunk"),          # advspec_append_tail: one prompt chunk per tail
+             ("persona_per_opponent_stepped", per, None, "step"))  # A/B: tails through the decode step
     row = {"rank": D.rank}
-    for label, panel, persona in cases:
+    for label, panel, persona, impl in cases:
         wall, res, before = 0.0, [], {}
+        os.environ["ADVSPEC_TAIL_IMPL"] = impl or "chunk"
         for rep in range(2):  # the first round may re-create the engine (larger suffix KV) and captures the graph
             before = dict(runtime.PREFIXES.stats)
             D.barrier()
@@ -461,13 +464,14 @@ def section_personas(args, D, peaks):
         toks = sum(r.output_tokens for r in res)
         row[label] = {"wall_s": wall, "tokens": toks, "tokens_per_s": toks / wall if wall > 0 else None,
                       "input_tokens": sorted(r.input_tokens for r in res), "tokens_prefilled": prefilled,
-                      "tail_steps": max(r.input_tokens for r in res) - prefilled if res else None,
+                      "longest_tail": max(r.input_tokens for r in res) - prefilled if res else None,
                       "prefills": after["full"] - before.get("full", 0), "errors": [r.error for r in res if r.error],
                       **st}
+    os.environ.pop("ADVSPEC_TAIL_IMPL", None)
     rows = D.gather(row)
     out = {"workload": "3 x Llama-3-8B, 4,096-token PRD, %d new tokens each; persona per opponent vs one for the "
                        "panel; one panel per rank" % args.gen, "per_rank": rows}
-    for label, _, _ in cases:
+    for label, _, _, _ in cases:
         wall = max(r[label]["wall_s"] for r in rows)
         out[label + "_tokens_per_s"] = sum(r[label]["tokens"] for r in rows) / wall if wall > 0 else None
     return out

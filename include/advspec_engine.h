@@ -176,6 +176,18 @@ advspec_status advspec_fork(advspec_engine *e, int32_t prefix_id,
                             int32_t n_seqs, const uint64_t *seeds,
                             int32_t *seq_ids);
 
+/* Give ONE freshly forked opponent more prompt tokens of its own: `tokens[0..n_tokens)` continue the shared
+ * prefix for this opponent only (a per-opponent persona or instruction behind the common document — the
+ * reference has one `--persona` for the whole panel, debate.py:835).  The tail runs as a
+ * prompt chunk (GEMM-shaped, one pass over the weights) at positions prefix_len.. against the prefix KV; its
+ * K/V becomes the first n_tokens entries of the opponent's own KV and the next-token logits after it are the
+ * ones `advspec_decode` samples this opponent's first token from.  Call it for every opponent of the coming
+ * decode batch, in batch order, directly after the fork; the shared prefix and the other opponents are
+ * untouched.  n_tokens counts against the opponent's max_new_tokens capacity; prefix_len + n_tokens must fit
+ * max_prefix_tokens (the chunk's K/V is staged behind the prefix). */
+advspec_status advspec_append_tail(advspec_engine *e, int32_t seq_id,
+                                   const int32_t *tokens, int32_t n_tokens);
+
 /* Batched autoregressive decode of the forked opponents: up to max_new tokens
  * each (`max_tokens`, models.py:620), sampling at `temperature` (0 = greedy),
  * stopping an opponent at eos_id (< 0: never).  out_tokens is [n][max_new]

@@ -162,17 +162,20 @@ def test_prefix_reuse_across_calls_matches_a_full_prefill(cuda_device, diag, mon
     assert r2[0].input_tokens > r1[0].input_tokens
 
 
-def test_per_opponent_tails_match_hf_and_share_one_prefill(cuda_device, diag, monkeypatch):
+@pytest.mark.parametrize("impl", ["chunk", "step"])
+def test_per_opponent_tails_match_hf_and_share_one_prefill(cuda_device, diag, monkeypatch, impl):
     """opponents whose prompts differ only at the end (per-opponent personas) share ONE
-    prefill of the common tokens; each opponent's own tail is teacher-forced through the batched decode step,
-    right-aligned, with tails of different lengths (37 / 1 / 12 tokens: the batch is 1, then 2, then 3
-    opponents wide and every opponent sits at a different position).  The logits each opponent samples its
-    first token from must match an HF forward of ITS full prompt, and greedy decoding must continue from
-    them within the stated tolerance."""
+    prefill of the common tokens; each opponent's own tail (37 / 1 / 12 tokens) is fed after the fork — as one
+    prompt chunk per opponent whose K/V moves into the opponent's own KV (`advspec_append_tail`, default), or
+    token by token through the batched decode step, right-aligned (the batch is 1, then 2, then 3 opponents
+    wide).  Either way every opponent then sits at a different position, the logits it samples its first
+    token from must match an HF forward of ITS full prompt, greedy decoding must continue from them within
+    the stated tolerance, and the shared prefix must be untouched."""
     from oracle import hf_oracle
     from tests.gpu_util import TOL_MAX, TOL_RMS, make_engine, rel_errors
     import numpy as np
 
+    monkeypatch.setenv("ADVSPEC_TAIL_IMPL", impl)
     spec, model, e = make_engine("tiny-llama-128", 41, max_prefix=2048, max_new=128)
     rng = np.random.default_rng(8)
     head = rng.integers(0, spec.vocab_size, 700).tolist()
@@ -182,24 +185,41 @@ def test_per_opponent_tails_match_hf_and_share_one_prefill(cuda_device, diag, mo
     assert shared == head and tails == tails_in
     pid = e.prefill(shared)
     ids = e.fork(pid, [1, 2, 3])
-    assert runtime.step_tails(e, ids, tails) == 37
+    runtime.feed_tails(e, ids, tails)
     lg = e.get_logits(3)
     worst = (0.0, 0.0)
     for i in range(3):
         mx, rms = rel_errors(lg[i], hf_oracle.hf_logits(model, prompts[i])[-1])
         worst = (max(worst[0], mx), max(worst[1], rms))
-    diag["persona_tails/tiny-llama-128"] = {"max": worst[0], "rms": worst[1]}
+    diag[f"persona_tails/{impl}/tiny-llama-128"] = {"max": worst[0], "rms": worst[1]}
     assert worst[0] < TOL_MAX and worst[1] < TOL_RMS, worst
+    if impl == "chunk":
+        with pytest.raises(Exception):
+            e.append_tail(ids[0], [1, 2])  # a tail directly follows the fork: this opponent already has one
     res = e.decode(ids, 6, temperature=0.0)
     assert res.lens == [6, 6, 6]
     for i in range(3):
-        assert res.tokens[i][0] == int(lg[i].argmax())  # token 0 comes from the last tail step's logits
+        assert res.tokens[i][0] == int(lg[i].argmax())  # token 0 comes from the logits after the tail
         hist = list(prompts[i])
         for tok in res.tokens[i]:
             ref = hf_oracle.hf_logits(model, hist)[-1]
             assert ref.max() - ref[tok] <= TOL_MAX * ref.std(), (i, tok, int(ref.argmax()))
             hist.append(tok)
+    # the prefix is as it was: a new opponent forked from it continues the SHARED prompt
+    e.release_seqs(ids)
+    (again,) = e.fork(pid, [9])
+    e.decode_step([again], [5])
+    mx, rms = rel_errors(e.get_logits(1)[0], hf_oracle.hf_logits(model, head + [5])[-1])
+    assert mx < TOL_MAX and rms < TOL_RMS, (mx, rms)
+    if impl == "chunk":
+        (late,) = e.fork(pid, [10])
+        with pytest.raises(Exception):
+            e.append_tail(late, list(range(129)))  # beyond the opponent's own KV capacity (max_new 128)
+        with pytest.raises(Exception):
+            e.append_tail(7, [1])  # not forked
     e.close()
+    if impl == "step":
+        return
 
     # through seam B2: three personas, one prefill, one decode batch of three
     monkeypatch.setattr(models.time, "sleep", lambda s: None)

@@ -27,6 +27,11 @@ class StepEngine(FakeEngine):
         assert len(ids) == len(forced) >= 1
         self.calls.append(("step", tuple(ids), tuple(forced)))
 
+    def append_tail(self, sid, tokens):
+        self._alive()
+        assert len(tokens) >= 1
+        self.calls.append(("tail", sid, len(tokens)))
+
     def decode(self, ids, max_new, temperature=0.7, eos_id=-1):
         self.calls.append(("decode", tuple(ids), max_new))
         return super().decode(ids, max_new, temperature, eos_id)
@@ -101,7 +106,24 @@ def test_tails_are_right_aligned_and_the_last_step_carries_everyone_in_fork_orde
     assert r.steps == [([10], [1]), ([10, 12], [2, 4]), ([10, 11, 12], [3, 7, 5])]
 
 
-def test_panel_with_personas_is_one_prefill_one_batch(step_engine):
+def test_panel_with_personas_feeds_each_tail_as_one_chunk_by_default(step_engine):
+    spec = resolve("tiny-llama")
+    doc = "alpha beta gamma delta " * 300
+    system, users = envelope.build_panel_messages(doc, 1, "prd", False, None,
+                                                  ["security-engineer", "oncall-engineer", None])
+    out = runtime.generate_group(spec, 0, system, users, 3, [1, 2, 3], 8000, 0.7)
+    e = FakeEngine.made[-1]
+    kinds = [c[0] for c in e.calls]
+    assert kinds == ["prefill", "fork", "tail", "tail", "tail", "decode"]
+    shared = e.calls[0][1]
+    assert [c[1:] for c in e.calls if c[0] == "tail"] == [(10 + i, g.prompt_tokens - shared) for i, g in enumerate(out)]
+    assert e.calls[-1][:2] == ("decode", (10, 11, 12))
+    assert e.max_prefix >= max(g.prompt_tokens for g in out)  # the chunk's K/V is staged behind the prefix
+    assert e.max_new >= 4 + max(g.prompt_tokens for g in out) - shared
+
+
+def test_panel_with_personas_is_one_prefill_one_batch(step_engine, monkeypatch):
+    monkeypatch.setenv("ADVSPEC_TAIL_IMPL", "step")
     spec = resolve("tiny-llama")
     doc = "alpha beta gamma delta " * 300
     system, users = envelope.build_panel_messages(doc, 1, "prd", False, None,
@@ -131,7 +153,7 @@ def test_prompts_that_differ_early_fall_back_to_a_prefill_each(step_engine):
     out = runtime.generate_group(spec, 0, "SYS", users, 3, [1, 2, 3], 8000, 0.7)
     e = FakeEngine.made[-1]
     kinds = [c[0] for c in e.calls]
-    assert "step" not in kinds and kinds.count("decode") == 2
+    assert "step" not in kinds and "tail" not in kinds and kinds.count("decode") == 2
     assert sorted(c[1] for c in e.calls if c[0] == "fork") == [1, 2]  # the two identical prompts share a batch
     assert out[0].prompt_tokens == out[2].prompt_tokens != out[1].prompt_tokens
     with pytest.raises(ValueError):
@@ -195,7 +217,7 @@ def test_seam_b1_coalesces_calls_whose_user_messages_differ(step_engine, monkeyp
     [t.join() for t in ts]
     e = FakeEngine.made[-1]
     kinds = [c[0] for c in e.calls]
-    assert kinds.count("prefill") == 1 and kinds.count("decode") == 1 and "step" in kinds
+    assert kinds.count("prefill") == 1 and kinds.count("decode") == 1 and kinds.count("tail") == 3
     assert all(o.usage.completion_tokens == 4 for o in outs)
     assert outs[0].usage.prompt_tokens == outs[2].usage.prompt_tokens < outs[1].usage.prompt_tokens
 
@@ -223,7 +245,10 @@ def test_bench_personas_section_reports_both_layouts(step_engine, monkeypatch):
     row = rec["per_rank"][0]
     one, per = row["one_persona_for_the_panel"], row["persona_per_opponent"]
     assert one["errors"] == [] and per["errors"] == [] and one["tokens"] == per["tokens"] == 12
-    assert len(set(one["input_tokens"])) == 1 and one["tail_steps"] == 0
-    assert len(set(per["input_tokens"])) == 3 and per["tail_steps"] == per["input_tokens"][-1] - per["tokens_prefilled"] > 0
+    assert len(set(one["input_tokens"])) == 1 and one["longest_tail"] == 0
+    assert len(set(per["input_tokens"])) == 3 and per["longest_tail"] == per["input_tokens"][-1] - per["tokens_prefilled"] > 0
     assert per["prefills"] == 1 and per["decode_batch"] == 3
+    kinds = [c[0] for c in FakeEngine.made[-1].calls]
+    assert kinds.count("tail") == 6 and kinds.count("step") == 2 * per["longest_tail"]  # chunk case, then stepped
+    assert row["persona_per_opponent_stepped"]["tokens"] == 12 and "ADVSPEC_TAIL_IMPL" not in __import__("os").environ
     assert rec["persona_per_opponent_tokens_per_s"] > 0 and rec["one_persona_for_the_panel_tokens_per_s"] > 0
