@@ -252,3 +252,21 @@ def test_bench_personas_section_reports_both_layouts(step_engine, monkeypatch):
     assert kinds.count("tail") == 6 and kinds.count("step") == 2 * per["longest_tail"]  # chunk case, then stepped
     assert row["persona_per_opponent_stepped"]["tokens"] == 12 and "ADVSPEC_TAIL_IMPL" not in __import__("os").environ
     assert rec["persona_per_opponent_tokens_per_s"] > 0 and rec["one_persona_for_the_panel_tokens_per_s"] > 0
+
+
+def test_more_opponents_than_one_batch_share_the_prefix_across_batches(step_engine):
+    """Ten opponents, two personas alternating: two decode batches (8 + 2); the second batch's shared prefix
+    is the first one's, so it is re-armed, not prefilled again."""
+    spec = resolve("tiny-llama")
+    doc = "alpha beta gamma delta " * 300
+    people = ["security-engineer", "oncall-engineer"] * 5
+    system, users = envelope.build_panel_messages(doc, 1, "prd", False, None, people)
+    out = runtime.generate_group(spec, 0, system, users, 10, list(range(10)), 8000, 0.7)
+    e = FakeEngine.made[-1]
+    kinds = [c[0] for c in e.calls]
+    assert kinds.count("prefill") == 1 and [c[1] for c in e.calls if c[0] == "fork"] == [8, 2]
+    assert kinds.count("tail") == 10 and kinds.count("decode") == 2
+    ext = [c for c in e.calls if c[0] == "extend"]
+    assert len(ext) == 1 and ext[0][2] == 0  # batch 2: same shared tokens -> re-armed, nothing prefilled
+    assert len(out) == 10 and all(g is not None and g.completion_tokens == 4 for g in out)
+    assert out[0].prompt_tokens == out[2].prompt_tokens != out[1].prompt_tokens
