@@ -43,6 +43,7 @@ def test_tensor_parallel_matches_hf_and_the_unsplit_engine(world):
         tol_max = 0.12 if name.startswith("llama-3-70b") else 0.08
         assert r["prefill_max_over_std"] < tol_max and r["prefill_rms_over_std"] < 0.02, r
         assert r["decode_max_over_std"] < tol_max, r
+        assert r["tails_max_over_std"] < tol_max and r["tail_first_tokens_are_argmax"], r  # advspec_append_tail
         assert r["ranks_identical"], r
         # the all-reduce changes the summation order, so a near-tie may flip a token; most must agree
         assert r["greedy_token_agreement"] >= 0.75 and r["sampled_token_agreement"] >= 0.5, r

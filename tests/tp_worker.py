@@ -55,6 +55,15 @@ def main():
         pid = e.prefill(prompt)
         ids = e.fork(pid, [7])
         greedy = e.decode(ids, 24, temperature=0.0).tokens
+        # per-opponent prompt tails (advspec_append_tail): the prompt's first 150 tokens are shared, opponent 0
+        # continues with tokens 150..199, opponent 1 with 150..179 — the logits after each tail are those of
+        # the same sequence at positions 199 / 179
+        pid = e.prefill(prompt[:150])
+        ids = e.fork(pid, [3, 4])
+        e.append_tail(ids[0], prompt[150:200])
+        e.append_tail(ids[1], prompt[150:180])
+        tails = gather(e.get_logits(2))
+        tail_tokens = e.decode(ids, 8, temperature=0.0).tokens
         e.close()
         res = {}
         if rank == 0:
@@ -67,6 +76,10 @@ def main():
                 for b in range(2):
                     dmax = max(dmax, float(np.abs(dec[i][b] - want[200 + i]).max() / std))
             res["decode_max_over_std"] = dmax
+            res["tails_max_over_std"] = float(max(np.abs(tails[0] - want[199]).max(),
+                                                  np.abs(tails[1] - want[179]).max()) / std)
+            res["tail_first_tokens_are_argmax"] = bool(tail_tokens[0][0] == int(tails[0].argmax()) and
+                                                       tail_tokens[1][0] == int(tails[1].argmax()))
             # the unsplit engine on this GPU, same seeds
             e1 = eng.Engine(spec, dev, 256, 64, 4)
             e1.set_rope_inv_freq(hf_oracle.rope_inv_freq(model))
@@ -80,7 +93,7 @@ def main():
             res["sampled_token_agreement"] = sum(a == b for x, y in zip(s1, sampled) for a, b in zip(x, y)) / tot
             res["greedy_token_agreement"] = sum(a == b for a, b in zip(g1[0], greedy[0])) / len(g1[0])
         # every rank must have produced the same tokens
-        mine = torch.tensor([t for row in sampled for t in row] + greedy[0], dtype=torch.int64)
+        mine = torch.tensor([t for row in sampled + tail_tokens for t in row] + greedy[0], dtype=torch.int64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         res["ranks_identical"] = bool(all(torch.equal(allr[0], a) for a in allr))
