@@ -15,7 +15,8 @@ reps = int(os.environ.get("AB_REPS", "3"))
 for rnd in range(2):
     for v in variants:
         for k in ("ADVSPEC_X_SMEM_MAX", "ADVSPEC_ATTN_MIN_SPLIT", "ADVSPEC_GEMV_IMPL", "ADVSPEC_ATTN_IMPL",
-                  "ADVSPEC_GEMM_NARROW", "ADVSPEC_NO_PDL", "ADVSPEC_ATTN_PREFILL_TC", "ADVSPEC_CHAIN", "ADVSPEC_L2_EVICT_FIRST", "ADVSPEC_GEMV_BALANCE", "ADVSPEC_PREFILL_CHUNK"):
+                  "ADVSPEC_GEMM_NARROW", "ADVSPEC_GEMM_SPLITK", "ADVSPEC_GEMM_BAND_MB", "ADVSPEC_NO_PDL", "ADVSPEC_NO_GRAPH",
+                  "ADVSPEC_ATTN_PREFILL_TC", "ADVSPEC_L2_EVICT_FIRST", "ADVSPEC_PREFILL_CHUNK"):
             os.environ.pop(k, None)
         os.environ.update({k: str(x) for k, x in v.items()})
         e = eng.Engine(spec, 0, 5120, 300, 8)
